@@ -1,0 +1,293 @@
+// Context management, error reporting and the small bandwidth-bound kernels of libdmvae_b200:
+// input staging, Adam (TF semantics), data-parallel reduce+Adam over peer memory, evaluation helpers.
+#include "common.cuh"
+
+static thread_local char g_err[1024] = "";
+
+void dmvae_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+extern "C" int dmvae_abi_version(void) { return DMVAE_B200_ABI_VERSION; }
+extern "C" const char* dmvae_last_error(void) { return g_err; }
+
+extern "C" int dmvae_ctx_create(int device, dmvae_ctx** out) {
+  DMVAE_CHECK_ARG(out != nullptr, "dmvae_ctx_create: out is NULL");
+  int n = 0;
+  DMVAE_CUDA(cudaGetDeviceCount(&n));
+  DMVAE_CHECK_ARG(device >= 0 && device < n, "dmvae_ctx_create: device %d out of range (%d devices)", device, n);
+  DMVAE_CUDA(cudaSetDevice(device));
+  dmvae_ctx* c = new dmvae_ctx();
+  c->device = device;
+  cudaDeviceProp p;
+  DMVAE_CUDA(cudaGetDeviceProperties(&p, device));
+  c->sm_count = p.multiProcessorCount;
+  c->cc_major = p.major;
+  c->cc_minor = p.minor;
+  // cuTensorMapEncodeTiled through the runtime so that libcuda is not a link-time dependency
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+      qres == cudaDriverEntryPointSuccess)
+    c->encode_tiled = fn;
+  (void)cudaGetLastError();
+  *out = c;
+  return DMVAE_OK;
+}
+
+extern "C" int dmvae_ctx_destroy(dmvae_ctx* ctx) {
+  delete ctx;
+  return DMVAE_OK;
+}
+
+extern "C" int64_t dmvae_ctx_launch_count(const dmvae_ctx* ctx) { return ctx ? ctx->launches : -1; }
+extern "C" int dmvae_ctx_has_tcgen05(const dmvae_ctx* ctx) {
+  return ctx && ctx->cc_major == 10 && ctx->encode_tiled != nullptr;
+}
+
+// ---------------------------------------------------------------------------------------------
+// zero / cast
+// ---------------------------------------------------------------------------------------------
+__global__ void zero_f32_kernel(float4* __restrict__ p4, float* __restrict__ tail, int64_t n4, int64_t ntail) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n4; i += stride) p4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (blockIdx.x == 0 && threadIdx.x < ntail) tail[threadIdx.x] = 0.f;
+}
+
+extern "C" int dmvae_zero_f32(dmvae_ctx* ctx, float* p, int64_t n, void* stream) {
+  DMVAE_CHECK_ARG(ctx && p && n >= 0, "dmvae_zero_f32: bad arguments");
+  DMVAE_CHECK_ARG(((uintptr_t)p & 15) == 0, "dmvae_zero_f32: pointer must be 16-byte aligned");
+  if (n == 0) return DMVAE_OK;
+  int64_t n4 = n / 4;
+  int blocks = (int)min((int64_t)ctx->sm_count * 8, (n4 + 255) / 256 + 1);
+  zero_f32_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((float4*)p, p + n4 * 4, n4, n - n4 * 4);
+  DMVAE_LAUNCH_CHECK(ctx);
+  return DMVAE_OK;
+}
+
+__global__ void cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t n) {
+  int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x * 8;
+  for (; i + 8 <= n; i += stride) {
+    float v[8];
+    Vec8<float>::load(src + i, v);
+    Vec8<__nv_bfloat16>::store(dst + i, v);
+  }
+  if (i < n && i + 8 > n)
+    for (int64_t j = i; j < n; ++j) dst[j] = __float2bfloat16_rn(src[j]);
+}
+
+extern "C" int dmvae_cast_bf16(dmvae_ctx* ctx, const float* src, void* dst, int64_t n, void* stream) {
+  DMVAE_CHECK_ARG(ctx && src && dst && n >= 0, "dmvae_cast_bf16: bad arguments");
+  DMVAE_CHECK_ARG(((uintptr_t)src & 31) == 0 && ((uintptr_t)dst & 15) == 0, "dmvae_cast_bf16: misaligned pointers");
+  if (n == 0) return DMVAE_OK;
+  int blocks = (int)min((int64_t)ctx->sm_count * 8, (n / 8 + 255) / 256 + 1);
+  cast_bf16_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, (__nv_bfloat16*)dst, n);
+  DMVAE_LAUNCH_CHECK(ctx);
+  return DMVAE_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// input staging: X -> operand matrix with the ones column
+// ---------------------------------------------------------------------------------------------
+template <typename TX, typename TO>
+__global__ void stage_input_kernel(const TX* __restrict__ X, int64_t ldx, TO* __restrict__ A, int64_t lda, int rows,
+                                   int D) {
+  // one warp per row, lanes stride over the padded width
+  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int r = warp; r < rows; r += nwarps) {
+    const TX* x = X + (int64_t)r * ldx;
+    TO* a = A + (int64_t)r * lda;
+    for (int j = lane; j < (int)lda; j += 32) {
+      float v = j < D ? to_f32<TX>(x[j]) : (j == D ? 1.f : 0.f);
+      a[j] = from_f32<TO>(v);
+    }
+  }
+}
+
+extern "C" int dmvae_stage_input(dmvae_ctx* ctx, const void* X, int x_dtype, int64_t ldx, void* A0, int out_dtype,
+                                 int64_t ld_out, int rows, int D, void* stream) {
+  DMVAE_CHECK_ARG(ctx && X && A0, "dmvae_stage_input: NULL pointer");
+  DMVAE_CHECK_ARG(rows >= 0 && D > 0 && ldx >= D && ld_out > D, "dmvae_stage_input: need ldx >= D and ld_out > D");
+  if (rows == 0) return DMVAE_OK;
+  int blocks = min(ctx->sm_count * 8, (rows + 7) / 8);
+  cudaStream_t s = (cudaStream_t)stream;
+#define STAGE(TX, TO) stage_input_kernel<TX, TO><<<blocks, 256, 0, s>>>((const TX*)X, ldx, (TO*)A0, ld_out, rows, D)
+  if (x_dtype == DMVAE_F32 && out_dtype == DMVAE_F32) STAGE(float, float);
+  else if (x_dtype == DMVAE_F32 && out_dtype == DMVAE_BF16) STAGE(float, __nv_bfloat16);
+  else if (x_dtype == DMVAE_U8 && out_dtype == DMVAE_F32) STAGE(uint8_t, float);
+  else if (x_dtype == DMVAE_U8 && out_dtype == DMVAE_BF16) STAGE(uint8_t, __nv_bfloat16);
+  else if (x_dtype == DMVAE_BF16 && out_dtype == DMVAE_BF16) STAGE(__nv_bfloat16, __nv_bfloat16);
+  else if (x_dtype == DMVAE_BF16 && out_dtype == DMVAE_F32) STAGE(__nv_bfloat16, float);
+  else {
+    dmvae_set_error("dmvae_stage_input: unsupported dtype pair (%d -> %d)", x_dtype, out_dtype);
+    return DMVAE_ERR_INVALID;
+  }
+#undef STAGE
+  DMVAE_LAUNCH_CHECK(ctx);
+  return DMVAE_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Adam, TensorFlow semantics: theta -= lr_t * m / (sqrt(v) + eps)
+// 16 B read (p,g,m,v) + 12 B written (p,m,v) per parameter (+2 B bf16 copy, +4 B gradient clear).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void adam_update4(float4& p, const float4 g, float4& m, float4& v, float lr_t, float b1,
+                                             float b2, float eps, float gs) {
+  float* pp = &p.x;
+  float* mm = &m.x;
+  float* vv = &v.x;
+  const float* gg = &g.x;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float gi = gg[i] * gs;
+    mm[i] = b1 * mm[i] + (1.f - b1) * gi;
+    vv[i] = b2 * vv[i] + (1.f - b2) * gi * gi;
+    pp[i] -= lr_t * mm[i] / (sqrtf(vv[i]) + eps);
+  }
+}
+
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ params, float* __restrict__ grads,
+                                                    float* __restrict__ m, float* __restrict__ v,
+                                                    __nv_bfloat16* __restrict__ pbf, int64_t n4, float lr_t, float b1,
+                                                    float b2, float eps, float gs, int zero_grads) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n4; i += stride) {
+    float4 p = reinterpret_cast<float4*>(params)[i];
+    float4 g = reinterpret_cast<float4*>(grads)[i];
+    float4 mm = reinterpret_cast<float4*>(m)[i];
+    float4 vv = reinterpret_cast<float4*>(v)[i];
+    adam_update4(p, g, mm, vv, lr_t, b1, b2, eps, gs);
+    reinterpret_cast<float4*>(params)[i] = p;
+    reinterpret_cast<float4*>(m)[i] = mm;
+    reinterpret_cast<float4*>(v)[i] = vv;
+    if (zero_grads) reinterpret_cast<float4*>(grads)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (pbf) {
+      __nv_bfloat162 lo = __floats2bfloat162_rn(p.x, p.y), hi = __floats2bfloat162_rn(p.z, p.w);
+      uint2 w = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+      reinterpret_cast<uint2*>(pbf)[i] = w;
+    }
+  }
+}
+
+extern "C" int dmvae_adam(dmvae_ctx* ctx, float* params, float* grads, float* m, float* v, void* params_bf16, int64_t n,
+                          float lr_t, float beta1, float beta2, float eps, float grad_scale, int zero_grads,
+                          void* stream) {
+  DMVAE_CHECK_ARG(ctx && params && grads && m && v, "dmvae_adam: NULL pointer");
+  DMVAE_CHECK_ARG(n >= 0 && n % 4 == 0, "dmvae_adam: n (%lld) must be a multiple of 4 (flat padded buffer)", (long long)n);
+  DMVAE_CHECK_ARG((((uintptr_t)params | (uintptr_t)grads | (uintptr_t)m | (uintptr_t)v) & 15) == 0 &&
+                      ((uintptr_t)params_bf16 & 7) == 0,
+                  "dmvae_adam: buffers must be 16-byte aligned");
+  if (n == 0) return DMVAE_OK;
+  int64_t n4 = n / 4;
+  int blocks = (int)min((int64_t)ctx->sm_count * 8, (n4 + 255) / 256);
+  adam_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(params, grads, m, v, (__nv_bfloat16*)params_bf16, n4, lr_t,
+                                                         beta1, beta2, eps, grad_scale, zero_grads);
+  DMVAE_LAUNCH_CHECK(ctx);
+  return DMVAE_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// data parallel: reduce the peers' gradient shards over NVLink, Adam on the owned shard, write the
+// updated parameters into every replica (reduce-scatter + Adam + all-gather in one kernel).
+// The caller brackets the launch with a cross-rank barrier on each side.
+// ---------------------------------------------------------------------------------------------
+struct DpPeers {
+  const float* grads[8];
+  float* params[8];
+  __nv_bfloat16* pbf[8];
+};
+
+__global__ void __launch_bounds__(256) dp_reduce_adam_kernel(DpPeers peers, int rank, int world, float* __restrict__ m,
+                                                              float* __restrict__ v, int64_t begin4, int64_t end4,
+                                                              float lr_t, float b1, float b2, float eps) {
+  int64_t i = begin4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < end4; i += stride) {
+    // fixed summation order (rank 0 .. world-1) so that every step is reproducible
+    float4 g = reinterpret_cast<const float4*>(peers.grads[0])[i];
+    for (int r = 1; r < world; ++r) {
+      float4 t = reinterpret_cast<const float4*>(peers.grads[r])[i];
+      g.x += t.x; g.y += t.y; g.z += t.z; g.w += t.w;
+    }
+    float4 p = reinterpret_cast<float4*>(peers.params[rank])[i];
+    const int64_t li = i - begin4;
+    float4 mm = reinterpret_cast<float4*>(m)[li];
+    float4 vv = reinterpret_cast<float4*>(v)[li];
+    adam_update4(p, g, mm, vv, lr_t, b1, b2, eps, 1.f);
+    reinterpret_cast<float4*>(m)[li] = mm;
+    reinterpret_cast<float4*>(v)[li] = vv;
+    __nv_bfloat162 lo = __floats2bfloat162_rn(p.x, p.y), hi = __floats2bfloat162_rn(p.z, p.w);
+    uint2 w = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+    for (int r = 0; r < world; ++r) {
+      reinterpret_cast<float4*>(peers.params[r])[i] = p;
+      if (peers.pbf[r]) reinterpret_cast<uint2*>(peers.pbf[r])[i] = w;
+    }
+  }
+}
+
+extern "C" int dmvae_dp_reduce_adam(dmvae_ctx* ctx, int rank, int world, const float* const* grads_peers_host,
+                                    float* const* params_peers_host, void* const* params_bf16_peers_host, float* m,
+                                    float* v, int64_t n, int64_t shard_begin, int64_t shard_end, float lr_t, float beta1,
+                                    float beta2, float eps, void* stream) {
+  DMVAE_CHECK_ARG(ctx && grads_peers_host && params_peers_host && m && v, "dmvae_dp_reduce_adam: NULL pointer");
+  DMVAE_CHECK_ARG(world >= 1 && world <= 8 && rank >= 0 && rank < world, "dmvae_dp_reduce_adam: world %d rank %d", world, rank);
+  DMVAE_CHECK_ARG(shard_begin % 4 == 0 && shard_end % 4 == 0 && 0 <= shard_begin && shard_begin <= shard_end && shard_end <= n,
+                  "dmvae_dp_reduce_adam: shard [%lld,%lld) must be 4-aligned and inside [0,%lld)", (long long)shard_begin,
+                  (long long)shard_end, (long long)n);
+  DpPeers peers;
+  memset(&peers, 0, sizeof(peers));
+  for (int r = 0; r < world; ++r) {
+    peers.grads[r] = grads_peers_host[r];
+    peers.params[r] = params_peers_host[r];
+    peers.pbf[r] = params_bf16_peers_host ? (__nv_bfloat16*)params_bf16_peers_host[r] : nullptr;
+    DMVAE_CHECK_ARG(peers.grads[r] && peers.params[r], "dmvae_dp_reduce_adam: peer %d pointer is NULL", r);
+  }
+  if (shard_end == shard_begin) return DMVAE_OK;
+  int64_t n4 = (shard_end - shard_begin) / 4;
+  int blocks = (int)min((int64_t)ctx->sm_count * 8, (n4 + 255) / 256);
+  dp_reduce_adam_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(peers, rank, world, m, v, shard_begin / 4, shard_end / 4,
+                                                                   lr_t, beta1, beta2, eps);
+  DMVAE_LAUNCH_CHECK(ctx);
+  return DMVAE_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// evaluation: argmax + contingency matrix  (base_models.py:425-432, utils.py:22-30)
+// ---------------------------------------------------------------------------------------------
+__global__ void argmax_contingency_kernel(const float* __restrict__ scores, int64_t ld, int rows, int K,
+                                          const int32_t* __restrict__ classes, int n_labels,
+                                          int32_t* __restrict__ argmax_out, int32_t* __restrict__ counts) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  const float* s = scores + (int64_t)r * ld;
+  int best = 0;
+  float bv = s[0];
+  for (int k = 1; k < K; ++k) {   // np.argmax: first maximum wins
+    float x = s[k];
+    if (x > bv) { bv = x; best = k; }
+  }
+  if (argmax_out) argmax_out[r] = best;
+  if (counts && classes) {
+    int c = classes[r];
+    if (c >= 0 && c < n_labels) atomicAdd(&counts[best * n_labels + c], 1);
+  }
+}
+
+extern "C" int dmvae_argmax_contingency(dmvae_ctx* ctx, const float* scores, int64_t ld, int rows, int K,
+                                        const int32_t* classes, int n_labels, int32_t* argmax_out, int32_t* counts,
+                                        void* stream) {
+  DMVAE_CHECK_ARG(ctx && scores && K > 0 && ld >= K && rows >= 0, "dmvae_argmax_contingency: bad arguments");
+  if (rows == 0) return DMVAE_OK;
+  argmax_contingency_kernel<<<(rows + 255) / 256, 256, 0, (cudaStream_t)stream>>>(scores, ld, rows, K, classes, n_labels,
+                                                                                   argmax_out, counts);
+  DMVAE_LAUNCH_CHECK(ctx);
+  return DMVAE_OK;
+}

@@ -1,0 +1,174 @@
+// Mixture-of-experts head: gate-weighted mixture of per-expert softmax classifiers / linear regressors
+// and its backward (models.py:76-111, :149-163).  The expert logits pred[b, e*O+o] come from one dense
+// GEMM over all experts (the reference tiles the input E times, models.py:76-81).
+#include "common.cuh"
+
+namespace {
+
+constexpr int kMaxO = 32;
+constexpr float kEps0 = 1e-20f;
+
+template <typename TD>
+__global__ void __launch_bounds__(128) moe_kernel(const dmvae_moe_args a) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= a.rows) return;
+  const int E = a.E, O = a.O;
+  const float s = a.inv_global_batch;
+  const float* pred = a.pred + (int64_t)row * a.ld_pred;
+  const float* gate = a.gate + (int64_t)row * a.ld_gate;
+  const float* Y = a.Y + (int64_t)row * a.ldy;
+  TD* dpred = reinterpret_cast<TD*>(a.d_pred) + (int64_t)row * a.ld_dpred;
+  float* dgate = a.d_gate + (int64_t)row * a.ld_dgate;
+  float u[kMaxO];
+#pragma unroll
+  for (int o = 0; o < kMaxO; ++o) u[o] = 0.f;
+
+  if (a.classification) {
+    // pass 1: unnormalised class probabilities u_o = sum_e gate_e softmax_o(pred_e)   (models.py:84-90)
+    for (int e = 0; e < E; ++e) {
+      const float* pe = pred + e * O;
+      float mx = pe[0];
+      for (int o = 1; o < O; ++o) mx = fmaxf(mx, pe[o]);
+      float den = 0.f;
+      for (int o = 0; o < O; ++o) den += expf(pe[o] - mx);
+      const float ge = gate[e] / den;
+#pragma unroll
+      for (int o = 0; o < kMaxO; ++o)
+        if (o < O) u[o] += ge * expf(pe[o] - mx);
+    }
+    float S = 0.f;
+    for (int o = 0; o < O; ++o) S += u[o];
+    // loss, prediction, d u
+    float loss = 0.f, dot = 0.f, best = -1.f;
+    int bi = 0;
+    float du[kMaxO];
+#pragma unroll
+    for (int o = 0; o < kMaxO; ++o) {
+      du[o] = 0.f;
+      if (o < O) {
+        float ys = u[o] / S;                                            // models.py:91-93
+        a.y_soft[(int64_t)row * O + o] = ys;
+        if (ys > best) { best = ys; bi = o; }
+        loss -= 1000.f * Y[o] * logf(ys + kEps0);                       // models.py:153-155
+        du[o] = -1000.f * s * Y[o] / (ys + kEps0);                      // d loss / d ys
+        dot += du[o] * u[o];
+      }
+    }
+#pragma unroll
+    for (int o = 0; o < kMaxO; ++o)
+      if (o < O) du[o] = du[o] / S - dot / (S * S);
+    a.pred_class[row] = bi;
+    // error summand: sum_o |Y - onehot(argmax)| / 2                                      models.py:95-103
+    float err = 0.f;
+    for (int o = 0; o < O; ++o) err += fabsf(Y[o] - (o == bi ? 1.f : 0.f));
+    a.per_sample[2 * (int64_t)row] = loss;
+    a.per_sample[2 * (int64_t)row + 1] = 0.5f * err;
+    // pass 2: gradients
+    for (int e = 0; e < E; ++e) {
+      const float* pe = pred + e * O;
+      float mx = pe[0];
+      for (int o = 1; o < O; ++o) mx = fmaxf(mx, pe[o]);
+      float den = 0.f;
+      for (int o = 0; o < O; ++o) den += expf(pe[o] - mx);
+      const float ge = gate[e];
+      float dg = 0.f, pdp = 0.f;
+      for (int o = 0; o < O; ++o) {
+        float p = expf(pe[o] - mx) / den;
+        dg += du[o] * p;
+        pdp += du[o] * ge * p;
+      }
+      dgate[e] = dg;
+      for (int o = 0; o < O; ++o) {
+        float p = expf(pe[o] - mx) / den;
+        dpred[e * O + o] = from_f32<TD>(p * (du[o] * ge - pdp));
+      }
+    }
+  } else {
+    // regression: Yhat_o = sum_e gate_e pred_eo                                          models.py:105-111
+    float err = 0.f, loss = 0.f;
+    float dy[kMaxO];
+#pragma unroll
+    for (int o = 0; o < kMaxO; ++o) {
+      dy[o] = 0.f;
+      if (o < O) {
+        float yh = 0.f;
+        for (int e = 0; e < E; ++e) yh += gate[e] * pred[e * O + o];
+        a.y_soft[(int64_t)row * O + o] = yh;
+        float df = yh - Y[o];
+        err += df * df;
+        loss += 0.5f * df * df;                                           // models.py:157-159
+        dy[o] = s * df;
+      }
+    }
+    if (a.pred_class) a.pred_class[row] = 0;
+    a.per_sample[2 * (int64_t)row] = loss;
+    a.per_sample[2 * (int64_t)row + 1] = err;          // error = mean_b(err_b) (= mean over B*O times O)
+    for (int e = 0; e < E; ++e) {
+      float dg = 0.f;
+      for (int o = 0; o < O; ++o) {
+        dg += dy[o] * pred[e * O + o];
+        dpred[e * O + o] = from_f32<TD>(dy[o] * gate[e]);
+      }
+      dgate[e] = dg;
+    }
+  }
+  for (int j = E * O; j < a.dpred_cols; ++j) dpred[j] = from_f32<TD>(0.f);
+}
+
+template <typename TD>
+__global__ void softmax_bwd_add_kernel(int rows, int K, const float* __restrict__ q, const float* __restrict__ dgate,
+                                       int64_t ld_dgate, TD* __restrict__ dlogits, int64_t ld, int accumulate, int cols) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= rows) return;
+  const float* qr = q + (int64_t)row * K;
+  const float* dg = dgate + (int64_t)row * ld_dgate;
+  float dot = 0.f;
+  for (int k = 0; k < K; ++k) dot += qr[k] * dg[k];
+  TD* d = dlogits + (int64_t)row * ld;
+  for (int k = 0; k < K; ++k) {
+    float v = qr[k] * (dg[k] - dot);
+    if (accumulate) v += to_f32<TD>(d[k]);
+    d[k] = from_f32<TD>(v);
+  }
+  if (!accumulate)
+    for (int k = K; k < cols; ++k) d[k] = from_f32<TD>(0.f);
+}
+
+}  // namespace
+
+extern "C" int dmvae_moe_fwd_bwd(dmvae_ctx* ctx, const dmvae_moe_args* a, void* stream) {
+  DMVAE_CHECK_ARG(ctx && a, "moe: NULL argument");
+  DMVAE_CHECK_ARG(a->rows >= 0 && a->E > 0 && a->O > 0 && a->O <= kMaxO, "moe: bad sizes rows=%d E=%d O=%d (O <= %d)", a->rows, a->E, a->O, kMaxO);
+  DMVAE_CHECK_ARG(a->pred && a->gate && a->Y && a->per_sample && a->y_soft && a->d_pred && a->d_gate, "moe: NULL pointer");
+  DMVAE_CHECK_ARG(!a->classification || a->pred_class, "moe: pred_class required for classification");
+  DMVAE_CHECK_ARG(a->ld_pred >= a->E * a->O && a->ld_dpred >= a->E * a->O && a->dpred_cols <= a->ld_dpred, "moe: leading dimensions too small");
+  if (a->rows == 0) return DMVAE_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  int blocks = (a->rows + 127) / 128;
+  if (a->dpred_dtype == DMVAE_F32) moe_kernel<float><<<blocks, 128, 0, st>>>(*a);
+  else if (a->dpred_dtype == DMVAE_BF16) moe_kernel<__nv_bfloat16><<<blocks, 128, 0, st>>>(*a);
+  else {
+    dmvae_set_error("moe: dpred_dtype %d unsupported", a->dpred_dtype);
+    return DMVAE_ERR_INVALID;
+  }
+  DMVAE_LAUNCH_CHECK(ctx);
+  return DMVAE_OK;
+}
+
+extern "C" int dmvae_softmax_bwd_add(dmvae_ctx* ctx, int rows, int K, const float* q, const float* d_gate, int64_t ld_dgate,
+                                     void* d_logits, int dtype, int64_t ld_dlogits, int accumulate, int cols, void* stream) {
+  DMVAE_CHECK_ARG(ctx && q && d_gate && d_logits && rows >= 0 && K > 0 && ld_dlogits >= K && cols <= ld_dlogits, "softmax_bwd_add: bad arguments");
+  if (rows == 0) return DMVAE_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  int blocks = (rows + 127) / 128;
+  if (dtype == DMVAE_F32)
+    softmax_bwd_add_kernel<float><<<blocks, 128, 0, st>>>(rows, K, q, d_gate, ld_dgate, (float*)d_logits, ld_dlogits, accumulate, cols);
+  else if (dtype == DMVAE_BF16)
+    softmax_bwd_add_kernel<__nv_bfloat16><<<blocks, 128, 0, st>>>(rows, K, q, d_gate, ld_dgate, (__nv_bfloat16*)d_logits, ld_dlogits, accumulate, cols);
+  else {
+    dmvae_set_error("softmax_bwd_add: dtype %d unsupported", dtype);
+    return DMVAE_ERR_INVALID;
+  }
+  DMVAE_LAUNCH_CHECK(ctx);
+  return DMVAE_OK;
+}

@@ -1,0 +1,654 @@
+"""Step engine: owns the flat parameter / gradient / Adam buffers and the padded activation buffers of one
+model, and sequences the sm_100a kernels of libdmvae_b200 for the forward, ELBO and backward passes.
+
+PyTorch is used for device memory and streams only; every arithmetic op on the path is a kernel of the
+C-ABI library (no torch math, no CPU fallback).
+
+Layout ("ones column", see include/dmvae_b200.h): a dense layer with n inputs and m outputs is one fp32
+matrix [pad(n), pad(m)] in the flat buffer, rows [0,n) = kernel, row n = bias, everything else zero;
+activations are [rows, pad(n)] with column n == 1.  pad(d) = round_up(d + 1, 64).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _abi
+from ._abi import BF16, F32, U8
+
+
+def pad_dim(d: int) -> int:
+    return ((d + 1 + 63) // 64) * 64
+
+
+def round64(d: int) -> int:
+    return ((d + 63) // 64) * 64
+
+
+@dataclass
+class VarView:
+    """Where one reference variable lives inside a padded layer matrix."""
+    layer: str
+    kind: str                 # "kernel" | "bias" | "table"
+    col0: int = 0
+    ncols: int = 0
+    shape: Tuple[int, ...] = ()
+    init: str = "xavier"      # xavier | zeros | normal
+    trainable: bool = True
+    transform: Optional[str] = None    # "moe_w" / "moe_b": reference layout differs from storage
+
+
+@dataclass
+class Layer:
+    name: str
+    n_in: int
+    in_pad: int
+    out_pad: int
+    n_valid: int              # ones-column structure of the OUTPUT (n_valid >= n_block: none)
+    n_block: int
+    offset: int = 0           # float offset in the flat buffer
+
+    @property
+    def size(self) -> int:
+        return self.in_pad * self.out_pad
+
+
+_TORCH_DT = {F32: torch.float32, BF16: torch.bfloat16, U8: torch.uint8}
+
+
+class AdamState:
+    """Slots of one tf.train.AdamOptimizer instance (base_models.py:102-110, :307-321)."""
+
+    def __init__(self, n: int, device, lr: float, beta1=0.9, beta2=0.999, eps=1e-8):
+        self.m = torch.zeros(n, dtype=torch.float32, device=device)
+        self.v = torch.zeros(n, dtype=torch.float32, device=device)
+        self.t = 0
+        self.lr, self.beta1, self.beta2, self.eps = lr, beta1, beta2, eps
+
+    def next_lr_t(self) -> float:
+        self.t += 1
+        return self.lr * math.sqrt(1.0 - self.beta2 ** self.t) / (1.0 - self.beta1 ** self.t)
+
+
+class Engine:
+    """Kernels + buffers for one DMVAE / VaDE model (optionally with an MoE expert head)."""
+
+    def __init__(self, *, model: str, input_type: str, input_dim: int, latent_dim: int, n_classes: int,
+                 trunk: Tuple[int, ...], head: int, decoder: Tuple[int, ...], name: str,
+                 gemm_dtype: str = "bf16", device=None, seed: int = 0, max_rows: int = 4096,
+                 cluster_sample: bool = False, temperature: float = 1.0, decoded_dtype: Optional[str] = None,
+                 moe: Optional[dict] = None, split_k_wgrad: Optional[int] = None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("dmvae_b200 needs a CUDA device: there is no CPU fallback")
+        if input_type not in ("binary", "real"):
+            raise NotImplementedError(input_type)                      # base_models.py:84-85
+        if model not in ("dmvae", "vade"):
+            raise NotImplementedError(model)
+        self.lib = _abi.load()
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.model, self.input_type, self.name = model, input_type, name
+        self.D, self.L, self.K = input_dim, latent_dim, n_classes
+        self.trunk, self.head, self.decoder = tuple(trunk), head, tuple(decoder)
+        self.cluster_sample, self.temperature = cluster_sample, float(temperature)
+        self.dt = {"bf16": BF16, "fp32": F32, "f32": F32}[gemm_dtype]
+        self.tdt = _TORCH_DT[self.dt]
+        self.dec_dt = self.dt if decoded_dtype is None else {"bf16": BF16, "fp32": F32, "f32": F32}[decoded_dtype]
+        if self.dt == F32:
+            self.dec_dt = F32
+        self.moe = moe
+        self.seed = seed
+        self.noise_seed = seed + 2
+        self.step_count = 0
+        self.split_k_wgrad = split_k_wgrad
+        self.world, self.rank = 1, 0
+        ctx = C.c_void_p()
+        _abi.check(self.lib.dmvae_ctx_create(self.device.index or 0, C.byref(ctx)))
+        self.ctx = ctx
+        if self.dt == BF16 and not self.lib.dmvae_ctx_has_tcgen05(self.ctx):
+            raise RuntimeError("gemm_dtype='bf16' needs an sm_100 (B200) device with TMA; no fallback exists")
+        self._build_layers()
+        self._alloc_params()
+        self.max_rows = 0
+        self._alloc_activations(max_rows)
+        self.init_variables(seed)
+
+    # ------------------------------------------------------------------------------------------
+    # layer table
+    # ------------------------------------------------------------------------------------------
+    def _build_layers(self):
+        D, L, K, n = self.D, self.L, self.K, self.name
+        self.layers: Dict[str, Layer] = {}
+        self.vars: Dict[str, VarView] = {}
+        e, d = n + "/encoder_network", n + "/decoder_network"
+
+        def add(name, n_in, n_out_pad, n_valid, n_block):
+            self.layers[name] = Layer(name, n_in, pad_dim(n_in), n_out_pad, n_valid, n_block)
+
+        def dense_vars(layer, kname, bname, n_in, col0, ncols, bias_shape, bias_init):
+            self.vars[kname] = VarView(layer, "kernel", col0, ncols, (n_in, ncols), "xavier")
+            self.vars[bname] = VarView(layer, "bias", col0, ncols, bias_shape, bias_init)
+
+        if self.model == "dmvae":
+            h1, h2 = self.trunk
+            hh = self.head
+            add("enc1", D, pad_dim(h1), h1, pad_dim(h1))
+            dense_vars("enc1", e + "/dense/kernel", e + "/dense/bias", D, 0, h1, (h1,), "zeros")
+            add("enc2", h1, pad_dim(h2), h2, pad_dim(h2))
+            dense_vars("enc2", e + "/dense_1/kernel", e + "/dense_1/bias", h1, 0, h2, (h2,), "zeros")
+            hp = pad_dim(hh)
+            add("ench", h2, 2 * hp, hh, hp)                               # [hidden_z | hidden_c]
+            dense_vars("ench", e + "/z/dense/kernel", e + "/z/dense/bias", h2, 0, hh, (hh,), "zeros")
+            dense_vars("ench", e + "/c/dense/kernel", e + "/c/dense/bias", h2, hp, hh, (hh,), "zeros")
+            add("zh", hh, round64(2 * L), 1, 1)                           # [mean | log_var], fp32 out
+            dense_vars("zh", e + "/z/dense_1/kernel", e + "/z/dense_1/bias", hh, 0, L, (L,), "zeros")
+            dense_vars("zh", e + "/z/dense_2/kernel", e + "/z/dense_2/bias", hh, L, L, (L,), "zeros")
+            add("ch", hh, round64(K), 1, 1)                               # logits, fp32 out
+            dense_vars("ch", e + "/c/dense_1/kernel", e + "/c/dense_1/bias", hh, 0, K, (K,), "zeros")
+            self.enc_chain = ["enc1", "enc2"]
+            self.last_hidden = h2
+            # dead head reconstructed_Y_soft (base_models.py:251-253): kept as untrained host variables
+            self.dead_vars = {e + "/dense_2/kernel": (h2, 10), e + "/dense_2/bias": (10,)}
+        else:
+            prev = D
+            self.enc_chain = []
+            for i, h in enumerate(self.trunk):
+                nm = "enc%d" % (i + 1)
+                add(nm, prev, pad_dim(h), h, pad_dim(h))
+                dense_vars(nm, e + "/layers/layer_%d/weight" % (i + 1), e + "/layers/layer_%d/bias" % (i + 1), prev, 0,
+                           h, (1, h), "xavier")                          # FullyConnected bias is xavier (layers.py:27-28)
+                self.enc_chain.append(nm)
+                prev = h
+            add("zh", prev, round64(2 * L), 1, 1)
+            dense_vars("zh", e + "/z/dense/kernel", e + "/z/dense/bias", prev, 0, L, (L,), "zeros")
+            dense_vars("zh", e + "/z/dense_1/kernel", e + "/z/dense_1/bias", prev, L, L, (L,), "zeros")
+            self.last_hidden = prev
+            self.dead_vars = {}
+        prev = L
+        self.dec_chain = []
+        for i, h in enumerate(self.decoder):
+            nm = "dec%d" % (i + 1)
+            add(nm, prev, pad_dim(h), h, pad_dim(h))
+            dense_vars(nm, d + "/layers/layer_%d/weight" % (i + 1), d + "/layers/layer_%d/bias" % (i + 1), prev, 0, h,
+                       (1, h), "xavier")
+            self.dec_chain.append(nm)
+            prev = h
+        add("decx", prev, pad_dim(D), 1, 1)
+        dense_vars("decx", d + "/dense/kernel", d + "/dense/bias", prev, 0, D, (D,), "zeros")
+        if self.moe is not None:
+            E, O = self.moe["n_experts"], self.moe["output_dim"]
+            I = L if self.moe["featLearn"] else D
+            add("moe", I, round64(E * O), 1, 1)
+            pfx = self.moe["scope"]
+            self.vars[pfx + "/regression_weights"] = VarView("moe", "kernel", 0, E * O, (E, O, I), "normal", True, "moe_w")
+            self.vars[pfx + "/regression_biases"] = VarView("moe", "bias", 0, E * O, (O, E), "zeros", True, "moe_b")
+        # prior tables (priors.py:58-65) live at the end of the flat buffer
+        self.vars[n + "/representation/means"] = VarView("prior_means", "table", 0, L, (K, L), "normal")
+        self.vars[n + "/representation/log_vars"] = VarView("prior_log_vars", "table", 0, L, (K, L), "zeros")
+
+    def _alloc_params(self):
+        off = 0
+        for ly in self.layers.values():
+            ly.offset = off
+            off += ly.size
+        self.tab_size = ((self.K * self.L + 63) // 64) * 64
+        self.off_means = off
+        self.off_log_vars = off + self.tab_size
+        self.n_params = off + 2 * self.tab_size
+        dev = self.device
+        self.params = torch.zeros(self.n_params, dtype=torch.float32, device=dev)
+        self.grads = torch.zeros(self.n_params, dtype=torch.float32, device=dev)
+        self.params_op = torch.zeros(self.n_params, dtype=torch.bfloat16, device=dev) if self.dt == BF16 else None
+        self.optimizers: Dict[str, AdamState] = {}
+        self.dead_values = {}
+
+    def W(self, name: str, grad: bool = False, op: bool = False) -> torch.Tensor:
+        ly = self.layers[name]
+        buf = self.grads if grad else (self.params_op if (op and self.params_op is not None) else self.params)
+        return buf[ly.offset: ly.offset + ly.size].view(ly.in_pad, ly.out_pad)
+
+    def table(self, which: str, grad: bool = False) -> torch.Tensor:
+        off = self.off_means if which == "means" else self.off_log_vars
+        buf = self.grads if grad else self.params
+        return buf[off: off + self.K * self.L].view(self.K, self.L)
+
+    # ------------------------------------------------------------------------------------------
+    # variables (reference names)
+    # ------------------------------------------------------------------------------------------
+    def variable_names(self) -> List[str]:
+        return list(self.vars.keys()) + list(self.dead_vars.keys())
+
+    def trainable_size(self) -> int:
+        """Number of reference parameters that receive a gradient (4 373 014 for cfg1/2)."""
+        return int(sum(int(np.prod(v.shape)) for v in self.vars.values()))
+
+    def _view(self, vv: VarView, grad=False) -> torch.Tensor:
+        if vv.kind == "table":
+            return self.table("means" if vv.layer == "prior_means" else "log_vars", grad)
+        ly = self.layers[vv.layer]
+        Wm = self.W(vv.layer, grad)
+        if vv.kind == "kernel":
+            return Wm[: ly.n_in, vv.col0: vv.col0 + vv.ncols]
+        return Wm[ly.n_in, vv.col0: vv.col0 + vv.ncols]
+
+    def get_variable(self, name: str, grad: bool = False) -> np.ndarray:
+        if name in self.dead_vars:
+            return self.dead_values[name].copy()
+        vv = self.vars[name]
+        t = self._view(vv, grad).detach().cpu().numpy()
+        if vv.transform == "moe_w":          # storage [I, E*O] -> reference [E, O, I]
+            E, O, I = vv.shape
+            return np.ascontiguousarray(t.reshape(I, E, O).transpose(1, 2, 0))
+        if vv.transform == "moe_b":          # storage [E*O] -> reference [O, E]
+            O, E = vv.shape
+            return np.ascontiguousarray(t.reshape(E, O).T)
+        return t.reshape(vv.shape).copy()
+
+    def set_variable(self, name: str, value) -> None:
+        value = np.asarray(value, dtype=np.float32)
+        if name in self.dead_vars:
+            self.dead_values[name] = value.reshape(self.dead_vars[name]).copy()
+            return
+        vv = self.vars[name]
+        if tuple(value.shape) != tuple(vv.shape):
+            value = value.reshape(vv.shape)
+        if vv.transform == "moe_w":
+            E, O, I = vv.shape
+            value = value.transpose(2, 0, 1).reshape(I, E * O)
+        elif vv.transform == "moe_b":
+            value = value.T.reshape(-1)
+        view = self._view(vv)
+        view.copy_(torch.from_numpy(np.ascontiguousarray(value)).to(self.device).reshape(view.shape))
+        self._params_dirty = True
+
+    def load_variables(self, values: Dict[str, np.ndarray], strict: bool = False) -> None:
+        for k, v in values.items():
+            if k in self.vars or k in self.dead_vars:
+                self.set_variable(k, v)
+            elif strict:
+                raise KeyError(k)
+        self.sync_operand_copy()
+
+    def state_dict(self) -> Dict[str, np.ndarray]:
+        return {k: self.get_variable(k) for k in self.variable_names()}
+
+    def init_variables(self, seed: int) -> None:
+        """xavier-uniform kernels, zero dense biases, xavier FullyConnected biases, N(0,1) prior means, zero prior
+        log-variances (train.py:161, layers.py:25-28, priors.py:58-65).  Host RNG, one upload."""
+        rng = np.random.RandomState(seed)
+        for k, shape in self.dead_vars.items():
+            if len(shape) == 2:
+                a = math.sqrt(6.0 / (shape[0] + shape[1]))
+                self.dead_values[k] = rng.uniform(-a, a, size=shape).astype(np.float32)
+            else:
+                self.dead_values[k] = np.zeros(shape, np.float32)
+        for k, vv in self.vars.items():
+            shape = vv.shape
+            if vv.init == "xavier":
+                fan_in, fan_out = shape[-2], shape[-1]
+                a = math.sqrt(6.0 / (fan_in + fan_out))
+                val = rng.uniform(-a, a, size=shape).astype(np.float32)
+            elif vv.init == "normal":
+                val = rng.standard_normal(shape).astype(np.float32)
+            else:
+                val = np.zeros(shape, np.float32)
+            self.set_variable(k, val)
+        self.sync_operand_copy()
+
+    def sync_operand_copy(self) -> None:
+        """Refresh the bf16 operand copy of the parameters (after loading variables)."""
+        if self.params_op is not None:
+            _abi.check(self.lib.dmvae_cast_bf16(self.ctx, self.params.data_ptr(), self.params_op.data_ptr(),
+                                                self.n_params, self._stream()))
+        self._params_dirty = False
+
+    # ------------------------------------------------------------------------------------------
+    # activations
+    # ------------------------------------------------------------------------------------------
+    def _alloc_activations(self, rows: int):
+        if rows <= self.max_rows:
+            return
+        self.max_rows = rows
+        dev, t = self.device, self.tdt
+        B = rows
+        z = lambda cols, dt=t: torch.zeros(B, cols, dtype=dt, device=dev)
+        f32 = torch.float32
+        self.act: Dict[str, torch.Tensor] = {}
+        self.dact: Dict[str, torch.Tensor] = {}
+        self.act["x"] = z(pad_dim(self.D))
+        for nm in self.enc_chain + (["ench"] if self.model == "dmvae" else []) + self.dec_chain:
+            self.act[nm] = z(self.layers[nm].out_pad)
+            self.dact[nm] = z(self.layers[nm].out_pad)
+        self.zh = z(self.layers["zh"].out_pad, f32)                    # mean | log_var
+        self.dzh = z(self.layers["zh"].out_pad)
+        if self.model == "dmvae":
+            self.ch = z(self.layers["ch"].out_pad, f32)                # logits
+            self.dch = z(self.layers["ch"].out_pad)
+        self.zb = z(pad_dim(self.L))                                   # Z (operand dtype, ones column)
+        self.dz = z(pad_dim(self.L), f32)
+        self.decoded = z(pad_dim(self.D), _TORCH_DT[self.dec_dt])
+        self.ddecoded = z(pad_dim(self.D), _TORCH_DT[self.dec_dt])
+        self.eps = z(self.L, f32)
+        self.eps_in = z(self.L, f32)
+        self.gumbel_in = z(self.K, f32)
+        self.zeta = z(self.K, f32)
+        self.per_sample = z(4, f32)
+        self.qc = z(self.K, f32)
+        self.argmax = torch.zeros(B, dtype=torch.int32, device=dev)
+        self.dmean_kl = z(self.L, f32)
+        self.dlogvar_kl = z(self.L, f32)
+        self.dz_gamma = z(self.L, f32)
+        self.w_scratch = z(self.K, f32)
+        self.f_scratch = z(2 * self.L, f32)
+        self.loss_out = torch.zeros(4, dtype=f32, device=dev)
+        ws = int(self.lib.dmvae_elbo_reduce_workspace(B, self.L, self.K))
+        self.red_ws = torch.zeros(max(ws, 4), dtype=f32, device=dev)
+        self.x_stage: Dict[int, torch.Tensor] = {}
+        if self.moe is not None:
+            E, O = self.moe["n_experts"], self.moe["output_dim"]
+            self.moe_in = z(self.layers["moe"].in_pad)
+            self.moe_pred = z(self.layers["moe"].out_pad, f32)
+            self.moe_dpred = z(self.layers["moe"].out_pad)
+            self.moe_dgate = z(E, f32)
+            self.moe_ps = z(2, f32)
+            self.moe_ysoft = z(O, f32)
+            self.moe_cls = torch.zeros(B, dtype=torch.int32, device=dev)
+            self.moe_dinp = z(self.layers["moe"].in_pad, f32)
+            self.y_buf = z(O, f32)
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    # ------------------------------------------------------------------------------------------
+    # kernel wrappers
+    # ------------------------------------------------------------------------------------------
+    def _fwd(self, name, A, lda, Y, out_dt, act, rows, W=None, ldw=None, n_out=None, n_in_pad=None):
+        ly = self.layers[name]
+        Wt = self.W(name, op=True) if W is None else W
+        _abi.check(self.lib.dmvae_linear_fwd(self.ctx, self.dt, A.data_ptr(), lda, Wt.data_ptr(),
+                                             ly.out_pad if ldw is None else ldw, Y.data_ptr(), Y.stride(0), out_dt, rows,
+                                             ly.out_pad if n_out is None else n_out,
+                                             ly.in_pad if n_in_pad is None else n_in_pad, act, ly.n_valid, ly.n_block,
+                                             self._stream()))
+
+    def _wgrad(self, name, A, lda, dY, lddy, rows, n_out=None, col0=0, accumulate=None):
+        ly = self.layers[name]
+        dW = self.W(name, grad=True)
+        n_out = ly.out_pad if n_out is None else n_out
+        sk = self._pick_split_k(rows, ly.in_pad, n_out)
+        acc = 1 if sk > 1 else 0
+        if accumulate is not None:
+            acc = accumulate
+        _abi.check(self.lib.dmvae_linear_wgrad(self.ctx, self.dt, A.data_ptr(), lda, dY.data_ptr(), lddy,
+                                               dW.data_ptr() + 4 * col0, ly.out_pad, rows, ly.in_pad, n_out, acc, sk,
+                                               self._stream()))
+
+    def _pick_split_k(self, rows, m, n) -> int:
+        if self.dt != BF16:
+            return 1
+        if self.split_k_wgrad is not None:
+            return max(1, self.split_k_wgrad)
+        tiles = ((m + 127) // 128) * ((n + 127) // 128)
+        nkb = (rows + 63) // 64
+        sms = 148
+        sk = max(1, min(nkb, (2 * sms + tiles - 1) // tiles))
+        return sk
+
+    def _dgrad(self, name, dY, lddy, act_in, ld_act, dX, out_dt, rows, prev_valid, prev_block, W=None, ldw=None,
+               n_in_pad=None, n_out_pad=None):
+        ly = self.layers[name]
+        Wt = self.W(name, op=True) if W is None else W
+        _abi.check(self.lib.dmvae_linear_dgrad(self.ctx, self.dt, dY.data_ptr(), lddy, Wt.data_ptr(),
+                                               ly.out_pad if ldw is None else ldw,
+                                               act_in.data_ptr() if act_in is not None else None, ld_act,
+                                               dX.data_ptr(), dX.stride(0), out_dt, rows,
+                                               ly.in_pad if n_in_pad is None else n_in_pad,
+                                               ly.out_pad if n_out_pad is None else n_out_pad, prev_valid, prev_block,
+                                               self._stream()))
+
+    # ------------------------------------------------------------------------------------------
+    # input staging
+    # ------------------------------------------------------------------------------------------
+    def stage_input(self, X: torch.Tensor, rows: int) -> Tuple[torch.Tensor, int]:
+        """X: device tensor [rows, D] (float32 / uint8 / bfloat16).  Fills the operand matrix act['x']."""
+        xdt = {torch.float32: F32, torch.uint8: U8, torch.bfloat16: BF16}[X.dtype]
+        _abi.check(self.lib.dmvae_stage_input(self.ctx, X.data_ptr(), xdt, X.stride(0), self.act["x"].data_ptr(), self.dt,
+                                              self.act["x"].stride(0), rows, self.D, self._stream()))
+        return X, xdt
+
+    # ------------------------------------------------------------------------------------------
+    # forward
+    # ------------------------------------------------------------------------------------------
+    def encode(self, rows: int, heads=("z", "c")):
+        """Encoder trunk and heads (base_models.py:218-249 / :490-513)."""
+        a = self.act["x"]
+        for nm in self.enc_chain:
+            self._fwd(nm, a, a.stride(0), self.act[nm], self.dt, _abi.ACT_RELU, rows)
+            a = self.act[nm]
+        if self.model == "dmvae":
+            hp = self.layers["ench"].n_block
+            self._fwd("ench", a, a.stride(0), self.act["ench"], self.dt, _abi.ACT_RELU, rows)
+            h = self.act["ench"]
+            if "z" in heads:
+                self._fwd("zh", h, h.stride(0), self.zh, F32, _abi.ACT_NONE, rows)
+            if "c" in heads:
+                self._fwd("ch", h[:, hp:], h.stride(0), self.ch, F32, _abi.ACT_NONE, rows)
+        else:
+            self._fwd("zh", a, a.stride(0), self.zh, F32, _abi.ACT_NONE, rows)
+
+    def reparam(self, rows: int, eps_injected: bool, gumbel_injected: bool, row_offset: int = 0, step: Optional[int] = None):
+        ra = _abi.ReparamArgs()
+        ra.rows, ra.L, ra.K = rows, self.L, self.K
+        ra.mean = self.zh.data_ptr()
+        ra.log_var = self.zh.data_ptr() + 4 * self.L
+        ra.ld_zh = self.zh.stride(0)
+        want_zeta = self.model == "dmvae" and self.cluster_sample
+        ra.logits = self.ch.data_ptr() if want_zeta else None
+        ra.ld_logits = self.ch.stride(0) if want_zeta else 0
+        ra.eps_in = self.eps_in.data_ptr() if eps_injected else None
+        ra.gumbel_in = self.gumbel_in.data_ptr() if (gumbel_injected and want_zeta) else None
+        ra.seed, ra.step, ra.row_offset = self.noise_seed, self.step_count if step is None else step, row_offset
+        ra.tau = self.temperature
+        ra.Z_out, ra.z_dtype, ra.ld_z, ra.z_cols = self.zb.data_ptr(), self.dt, self.zb.stride(0), self.zb.shape[1]
+        ra.eps_out = self.eps.data_ptr()
+        ra.zeta_out = self.zeta.data_ptr() if want_zeta else None
+        _abi.check(self.lib.dmvae_reparam_fwd(self.ctx, C.byref(ra), self._stream()))
+
+    def decode(self, rows: int):
+        a = self.zb
+        for nm in self.dec_chain:
+            self._fwd(nm, a, a.stride(0), self.act[nm], self.dt, _abi.ACT_RELU, rows)
+            a = self.act[nm]
+        self._fwd("decx", a, a.stride(0), self.decoded, self.dec_dt, _abi.ACT_NONE, rows)
+
+    def _elbo_args(self, X, xdt, rows, kl_ratio, inv_global_batch, recon_scale=1.0) -> _abi.ElboArgs:
+        ea = _abi.ElboArgs()
+        ea.mode = _abi.MODE_VADE if self.model == "vade" else (
+            _abi.MODE_DMVAE_SAMPLED if self.cluster_sample else _abi.MODE_DMVAE)
+        ea.input_type = _abi.INPUT_BINARY if self.input_type == "binary" else _abi.INPUT_REAL
+        ea.rows, ea.D, ea.L, ea.K = rows, self.D, self.L, self.K
+        ea.X, ea.x_dtype, ea.ldx = X.data_ptr(), xdt, X.stride(0)
+        ea.decoded, ea.dec_dtype, ea.ld_dec = self.decoded.data_ptr(), self.dec_dt, self.decoded.stride(0)
+        ea.mean, ea.log_var, ea.ld_zh = self.zh.data_ptr(), self.zh.data_ptr() + 4 * self.L, self.zh.stride(0)
+        if self.model == "dmvae":
+            ea.logits, ea.ld_logits = self.ch.data_ptr(), self.ch.stride(0)
+            ea.d_logits, ea.dlogits_dtype = self.dch.data_ptr(), self.dt
+            ea.ld_dlogits, ea.dlogits_cols = self.dch.stride(0), self.dch.shape[1]
+        ea.eps, ea.ld_eps = self.eps.data_ptr(), self.eps.stride(0)
+        ea.zeta, ea.ld_zeta = self.zeta.data_ptr(), self.zeta.stride(0)
+        ea.tau = self.temperature
+        ea.prior_means = self.table("means").data_ptr()
+        ea.prior_log_vars = self.table("log_vars").data_ptr()
+        ea.kl_ratio, ea.inv_global_batch, ea.recon_scale = kl_ratio, inv_global_batch, recon_scale
+        ea.per_sample, ea.qc, ea.argmax = self.per_sample.data_ptr(), self.qc.data_ptr(), self.argmax.data_ptr()
+        ea.d_decoded, ea.ld_ddec, ea.ddec_cols = self.ddecoded.data_ptr(), self.ddecoded.stride(0), self.ddecoded.shape[1]
+        ea.d_mean_kl, ea.d_log_var_kl, ea.ld_dkl = self.dmean_kl.data_ptr(), self.dlogvar_kl.data_ptr(), self.L
+        ea.d_Z_gamma, ea.ld_dzg = self.dz_gamma.data_ptr(), self.L
+        ea.w_scratch, ea.f_scratch = self.w_scratch.data_ptr(), self.f_scratch.data_ptr()
+        return ea
+
+    def elbo(self, X, xdt, rows, kl_ratio=1.0, inv_global_batch=None, recon_scale=1.0, prior_grads=True):
+        """Fused ELBO forward + backward and its cross-sample reductions."""
+        s = (1.0 / rows) if inv_global_batch is None else inv_global_batch
+        ea = self._elbo_args(X, xdt, rows, kl_ratio, s, recon_scale)
+        st = self._stream()
+        _abi.check(self.lib.dmvae_elbo_fwd_bwd(self.ctx, C.byref(ea), st))
+        gm = self.table("means", grad=True).data_ptr() if prior_grads else None
+        gl = self.table("log_vars", grad=True).data_ptr() if prior_grads else None
+        _abi.check(self.lib.dmvae_elbo_reduce(self.ctx, C.byref(ea), gm, gl, 0, self.loss_out.data_ptr(),
+                                              self.red_ws.data_ptr(), st))
+
+    # ------------------------------------------------------------------------------------------
+    # backward
+    # ------------------------------------------------------------------------------------------
+    def backward(self, rows: int, dmean_extra: Optional[torch.Tensor] = None, train_decoder=True, train_z=True,
+                 train_c=True, train_trunk=True):
+        """Gradient GEMMs from d_decoded / d_logits / KL-side gradients back to every parameter."""
+        dt = self.dt
+        # ---- decoder ----
+        chain = self.dec_chain
+        a_last = self.act[chain[-1]]
+        if train_decoder or train_z:
+            if train_decoder:
+                self._wgrad("decx", a_last, a_last.stride(0), self.ddecoded, self.ddecoded.stride(0), rows)
+            ly_prev = self.layers[chain[-1]]
+            self._dgrad("decx", self.ddecoded, self.ddecoded.stride(0), a_last, a_last.stride(0), self.dact[chain[-1]], dt,
+                        rows, ly_prev.n_valid, ly_prev.n_block)
+            for i in range(len(chain) - 1, -1, -1):
+                nm = chain[i]
+                a_in = self.act[chain[i - 1]] if i > 0 else self.zb
+                dy = self.dact[nm]
+                if train_decoder:
+                    self._wgrad(nm, a_in, a_in.stride(0), dy, dy.stride(0), rows)
+                if i > 0:
+                    lp = self.layers[chain[i - 1]]
+                    self._dgrad(nm, dy, dy.stride(0), a_in, a_in.stride(0), self.dact[chain[i - 1]], dt, rows, lp.n_valid,
+                                lp.n_block)
+                else:
+                    # dZ: fp32, no ReLU mask (Z is not an activation output); columns >= L zeroed
+                    self._dgrad(nm, dy, dy.stride(0), None, 0, self.dz, F32, rows, self.L, self.dz.shape[1])
+        # ---- reparameterisation backward (priors.py:86-89) ----
+        if train_z:
+            _abi.check(self.lib.dmvae_reparam_bwd(
+                self.ctx, rows, self.L, self.dmean_kl.data_ptr(), self.dlogvar_kl.data_ptr(), self.L,
+                self.dz.data_ptr(), self.dz.stride(0),
+                self.dz_gamma.data_ptr() if self.model == "vade" else None, self.L,
+                self.eps.data_ptr(), self.zh.data_ptr() + 4 * self.L, self.zh.stride(0),
+                dmean_extra.data_ptr() if dmean_extra is not None else None,
+                dmean_extra.stride(0) if dmean_extra is not None else 0,
+                self.dzh.data_ptr(), dt, self.dzh.stride(0), self.dzh.shape[1], self._stream()))
+        # ---- encoder heads ----
+        if self.model == "dmvae":
+            h = self.act["ench"]
+            dh = self.dact["ench"]
+            hp = self.layers["ench"].n_block
+            hv = self.layers["ench"].n_valid
+            if train_z:
+                self._wgrad("zh", h, h.stride(0), self.dzh, self.dzh.stride(0), rows)
+                self._dgrad("zh", self.dzh, self.dzh.stride(0), h, h.stride(0), dh, dt, rows, hv, hp)
+            if train_c:
+                self._wgrad("ch", h[:, hp:], h.stride(0), self.dch, self.dch.stride(0), rows)
+                self._dgrad("ch", self.dch, self.dch.stride(0), h[:, hp:], h.stride(0), dh[:, hp:], dt, rows, hv, hp)
+            a_in = self.act[self.enc_chain[-1]]
+            if train_z and train_c:
+                self._wgrad("ench", a_in, a_in.stride(0), dh, dh.stride(0), rows)
+            elif train_c:      # prior pre-training: only the c-head columns (base_models.py:312-321)
+                self._wgrad("ench", a_in, a_in.stride(0), dh[:, hp:], dh.stride(0), rows, n_out=hp, col0=hp)
+            elif train_z:
+                self._wgrad("ench", a_in, a_in.stride(0), dh, dh.stride(0), rows, n_out=hp, col0=0)
+            if train_trunk:
+                lp = self.layers[self.enc_chain[-1]]
+                if train_z and train_c:
+                    self._dgrad("ench", dh, dh.stride(0), a_in, a_in.stride(0), self.dact[self.enc_chain[-1]], dt, rows,
+                                lp.n_valid, lp.n_block)
+                else:
+                    c0 = hp if train_c else 0
+                    Wsub = self.W("ench", op=True)[:, c0:]
+                    self._dgrad("ench", dh[:, c0:], dh.stride(0), a_in, a_in.stride(0), self.dact[self.enc_chain[-1]], dt,
+                                rows, lp.n_valid, lp.n_block, W=Wsub, ldw=self.layers["ench"].out_pad, n_out_pad=hp)
+        else:
+            if train_z:
+                a_in = self.act[self.enc_chain[-1]]
+                lp = self.layers[self.enc_chain[-1]]
+                self._wgrad("zh", a_in, a_in.stride(0), self.dzh, self.dzh.stride(0), rows)
+                self._dgrad("zh", self.dzh, self.dzh.stride(0), a_in, a_in.stride(0), self.dact[self.enc_chain[-1]], dt,
+                            rows, lp.n_valid, lp.n_block)
+        # ---- encoder trunk ----
+        if train_trunk:
+            ec = self.enc_chain
+            for i in range(len(ec) - 1, -1, -1):
+                nm = ec[i]
+                a_in = self.act[ec[i - 1]] if i > 0 else self.act["x"]
+                dy = self.dact[nm]
+                self._wgrad(nm, a_in, a_in.stride(0), dy, dy.stride(0), rows)
+                if i > 0:
+                    lp = self.layers[ec[i - 1]]
+                    self._dgrad(nm, dy, dy.stride(0), a_in, a_in.stride(0), self.dact[ec[i - 1]], dt, rows, lp.n_valid,
+                                lp.n_block)
+
+    # ------------------------------------------------------------------------------------------
+    # optimiser
+    # ------------------------------------------------------------------------------------------
+    def optimizer(self, key: str, lr: float) -> AdamState:
+        if key not in self.optimizers:
+            self.optimizers[key] = AdamState(self.n_params, self.device, lr)
+        return self.optimizers[key]
+
+    def zero_grads(self):
+        _abi.check(self.lib.dmvae_zero_f32(self.ctx, self.grads.data_ptr(), self.n_params, self._stream()))
+        self._grads_dirty = False
+
+    def adam(self, opt: AdamState, zero_grads: bool = True):
+        lr_t = opt.next_lr_t()
+        _abi.check(self.lib.dmvae_adam(self.ctx, self.params.data_ptr(), self.grads.data_ptr(), opt.m.data_ptr(),
+                                       opt.v.data_ptr(), self.params_op.data_ptr() if self.params_op is not None else None,
+                                       self.n_params, lr_t, opt.beta1, opt.beta2, opt.eps, 1.0, 1 if zero_grads else 0,
+                                       self._stream()))
+        if zero_grads:
+            self._grads_dirty = False
+
+    # ------------------------------------------------------------------------------------------
+    # whole steps
+    # ------------------------------------------------------------------------------------------
+    def forward_backward(self, X: torch.Tensor, rows: int, eps: Optional[torch.Tensor] = None,
+                         gumbel: Optional[torch.Tensor] = None, kl_ratio: float = 1.0, inv_global_batch=None,
+                         row_offset: int = 0, recon_scale: float = 1.0, backward: bool = True, mode: str = "all"):
+        """encoder -> reparam -> decoder -> fused ELBO (-> gradient GEMMs).  Results stay on the device."""
+        if rows > self.max_rows:
+            self._alloc_activations(rows)
+        if getattr(self, "_params_dirty", False):
+            self.sync_operand_copy()
+        if backward and getattr(self, "_grads_dirty", False):
+            self.zero_grads()                      # split-K wgrads accumulate into the gradient buffer
+        if eps is not None:
+            self.eps_in[:rows].copy_(eps.reshape(rows, self.L))
+        if gumbel is not None:
+            self.gumbel_in[:rows].copy_(gumbel.reshape(rows, self.K))
+        X, xdt = self.stage_input(X, rows)
+        self.encode(rows)
+        self.reparam(rows, eps is not None, gumbel is not None, row_offset)
+        self.decode(rows)
+        flags = dict(all=(True, True, True, True), vae=(True, True, False, True), prior=(False, False, True, False))[mode]
+        self.elbo(X, xdt, rows, kl_ratio, inv_global_batch, recon_scale, prior_grads=(mode == "all"))
+        if backward:
+            self.backward(rows, train_decoder=flags[0], train_z=flags[1], train_c=flags[2], train_trunk=flags[3])
+            self._grads_dirty = True
+
+    def train_step(self, X: torch.Tensor, rows: int, opt: AdamState, eps=None, gumbel=None, kl_ratio=1.0,
+                   mode: str = "all", recon_scale: float = 1.0):
+        """One optimisation step (VAE.train_op body, base_models.py:117-129).  Returns nothing; read loss_out."""
+        self.forward_backward(X, rows, eps, gumbel, kl_ratio, None, 0, recon_scale, True, mode)
+        self.adam(opt, zero_grads=True)
+        self.step_count += 1
+
+    def launches(self) -> int:
+        return int(self.lib.dmvae_ctx_launch_count(self.ctx))
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.lib.dmvae_ctx_destroy(self.ctx)
+            self.ctx = None
