@@ -645,6 +645,52 @@ class Engine:
         self.adam(opt, zero_grads=True)
         self.step_count += 1
 
+    def run_epoch(self, host: torch.Tensor, batch_size: int, opt: AdamState, kl_ratio: float = 1.0, mode: str = "all",
+                  max_steps: Optional[int] = None) -> float:
+        """One pass over a (pinned) host array [N, D]: per step an asynchronous host->device copy of the batch on a
+        copy stream (double-buffered, overlapping the previous step), the training step, and an asynchronous read of
+        its loss.  One synchronisation at the end.  Returns the mean batch loss (base_models.py:130)."""
+        N = host.shape[0]
+        nb = (N + batch_size - 1) // batch_size
+        if max_steps is not None:
+            nb = min(nb, max_steps)
+        dev = self.device
+        if batch_size > self.max_rows:
+            self._alloc_activations(batch_size)
+        key = (batch_size, host.dtype)
+        if getattr(self, "_epoch_key", None) != key:
+            self._epoch_key = key
+            self._copy_stream = torch.cuda.Stream(device=dev)
+            self._stage = [torch.empty(batch_size, self.D, dtype=host.dtype, device=dev) for _ in range(2)]
+            self._ready = [torch.cuda.Event() for _ in range(2)]
+            self._free = [torch.cuda.Event() for _ in range(2)]
+        if getattr(self, "_loss_log", None) is None or self._loss_log.shape[0] < nb:
+            self._loss_log = torch.zeros(nb, 4, dtype=torch.float32, device=dev)
+            self._loss_host = torch.zeros(nb, 4, dtype=torch.float32).pin_memory()
+        cur = torch.cuda.current_stream(dev)
+        klr, rs = kl_ratio, 1.0
+        if mode == "vae":
+            klr = 0.0
+        elif mode == "prior":
+            klr, rs = 1.0, 0.0
+        for i in range(nb):
+            b = i & 1
+            lo = i * batch_size
+            rows = min(batch_size, N - lo)
+            with torch.cuda.stream(self._copy_stream):
+                if i >= 2:
+                    self._copy_stream.wait_event(self._free[b])
+                self._stage[b][:rows].copy_(host[lo:lo + rows], non_blocking=True)
+                self._ready[b].record(self._copy_stream)
+            cur.wait_event(self._ready[b])
+            self.train_step(self._stage[b], rows, opt, None, None, klr, mode, rs)
+            self._loss_log[i].copy_(self.loss_out, non_blocking=True)
+            self._free[b].record(cur)
+        self._loss_host[:nb].copy_(self._loss_log[:nb], non_blocking=True)
+        cur.synchronize()
+        col = {"all": 3, "vae": 0, "prior": 3}[mode]
+        return float(self._loss_host[:nb, col].sum()) / nb
+
     def launches(self) -> int:
         return int(self.lib.dmvae_ctx_launch_count(self.ctx))
 

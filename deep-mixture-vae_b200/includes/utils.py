@@ -1,0 +1,210 @@
+"""Host-side utilities mirroring code/includes/utils.py: Gumbel noise, clustering accuracy, label generators,
+dataset loading and the batching iterators.
+
+The batching iterators keep the reference semantics (reshuffle every epoch, tail batch kept) but hold the
+data in ONE pinned host array and yield contiguous slices, so the training loop can issue an asynchronous
+host->device copy per batch instead of the reference's per-row Python append (utils.py:449-463).
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import numpy as np
+import torch
+from scipy.optimize import linear_sum_assignment
+
+
+def sample_gumbel(shape, eps=1e-20):
+    """includes/utils.py:17-19."""
+    U = np.random.uniform(0, 1, shape)
+    return -np.log(eps - np.log(U + eps))
+
+
+def hungarian_accuracy(d: np.ndarray, size: int) -> float:
+    """Accuracy under the best cluster->class assignment of contingency matrix d (utils.py:33-34;
+    sklearn's removed linear_assignment_ replaced by scipy's equivalent linear_sum_assignment)."""
+    r, c = linear_sum_assignment(d.max() - d)
+    return float(d[r, c].sum()) / (size * 1.0)
+
+
+def get_clustering_accuracy(weights, classes):
+    """includes/utils.py:22-34."""
+    weights = np.asarray(weights)
+    clusters = np.argmax(weights, axis=-1)
+    n_classes = weights.shape[1]
+    size = len(clusters)
+    d = np.zeros((n_classes, n_classes), dtype=np.int64)
+    np.add.at(d, (clusters, np.asarray(classes).astype(np.int64)), 1)
+    return hungarian_accuracy(d, size)
+
+
+def generate_regression_variable(dataset, output_dim):
+    """includes/utils.py:37-60."""
+    n_experts = dataset.n_classes
+    input_dim = dataset.train_data.shape[1]
+    biases = np.random.randn(output_dim, n_experts)
+    weights = np.random.randn(output_dim, input_dim, n_experts)
+    train_labels = np.swapaxes(np.matmul(dataset.train_data, weights), 0, 1) + biases
+    train_labels = train_labels[range(len(dataset.train_data)), :, dataset.train_classes]
+    test_labels = np.swapaxes(np.matmul(dataset.test_data, weights), 0, 1) + biases
+    test_labels = test_labels[range(len(dataset.test_data)), :, dataset.test_classes]
+    return train_labels, test_labels
+
+
+def generate_classification_variables(dataset):
+    """includes/utils.py:63-74."""
+    n_classes = dataset.n_classes
+    test_labels = np.zeros((len(dataset.test_classes), n_classes))
+    test_labels[np.arange(0, len(dataset.test_classes)), dataset.test_classes] = 1
+    train_labels = np.zeros((len(dataset.train_classes), n_classes))
+    train_labels[np.arange(0, len(dataset.train_classes)), dataset.train_classes] = 1
+    return train_labels, test_labels
+
+
+class _Bag:
+    pass
+
+
+def _synthetic(name, n_train, n_test, dim, binarised, n_classes=10, seed=1):
+    """X[b,d] = 1{u < 0.1307} (MNIST-shaped) or randint(0,256)/255 (CIFAR-shaped); labels b mod 10."""
+    rng = np.random.RandomState(seed)
+    ds = _Bag()
+
+    def make(n):
+        if binarised:
+            return (rng.uniform(size=(n, dim)) < 0.1307).astype(np.float32)
+        return (rng.randint(0, 256, size=(n, dim)) / 255.0).astype(np.float32)
+
+    ds.datagroup = name
+    ds.train_data, ds.test_data = make(n_train), make(n_test)
+    ds.train_classes = (np.arange(n_train) % n_classes).astype(np.int64)
+    ds.test_classes = (np.arange(n_test) % n_classes).astype(np.int64)
+    ds.n_classes, ds.input_dim, ds.input_type = n_classes, dim, "binary"
+    ds.sample_plot = ds.regeneration_plot = None
+    return ds
+
+
+def load_data(datagroup, output_dim=1, classification=True, **args):
+    """includes/utils.py:77-375.  The real corpora need downloads (no network here): ``spiral`` is generated
+    exactly as the reference does; ``synthetic_mnist`` / ``synthetic_cifar`` are the benchmark shapes;
+    the download-backed names raise NotImplementedError with a pointer to the synthetic ones."""
+    if datagroup == "spiral":
+        N_tr, N_ts, D, K = args.get("N_tr", 5000), args.get("N_ts", 1000), 2, args.get("K", 5)
+        ds = _Bag()
+        train_data, test_data = np.zeros((N_tr * K, D)), np.zeros((N_ts * K, D))
+        for data, N in ((train_data, N_tr), (test_data, N_ts)):
+            for j in range(K):
+                ix = range(N * j, N * (j + 1))
+                r = np.linspace(2.5, 10.0, N)
+                t = np.linspace(j * 1.25, (j + 1) * 1.25, N) + np.random.randn(N) * 0.05
+                data[ix] = np.c_[r * np.sin(t), r * np.cos(t)]
+        ds.datagroup = "spiral"
+        ds.test_data, ds.test_classes = test_data, np.arange(K).repeat(N_ts)
+        ds.train_data, ds.train_classes = train_data, np.arange(K).repeat(N_tr)
+        ds.n_classes, ds.input_dim, ds.input_type = 5, 2, "real"
+        ds.sample_plot = ds.regeneration_plot = None
+    elif datagroup in ("synthetic_mnist", "synthetic"):
+        ds = _synthetic("synthetic_mnist", args.get("n_train", 55000), args.get("n_test", 10000), 784, True)
+    elif datagroup == "synthetic_cifar":
+        ds = _synthetic("synthetic_cifar", args.get("n_train", 50000), args.get("n_test", 10000), 3072, False)
+    elif datagroup in ("mnist", "hhar", "cifar10", "reuters", "reuters10k"):
+        raise NotImplementedError("dataset %r needs a download (no network in this build); use 'synthetic_mnist', "
+                                  "'synthetic_cifar' or 'spiral', or pass your own arrays to Dataset" % datagroup)
+    else:
+        raise NotImplementedError
+    if classification:
+        ds.train_labels, ds.test_labels = generate_classification_variables(ds)
+    else:
+        ds.train_labels, ds.test_labels = generate_regression_variable(ds, output_dim)
+    return ds
+
+
+def _pinned(a: np.ndarray, dtype) -> torch.Tensor:
+    t = torch.from_numpy(np.ascontiguousarray(a, dtype=dtype))
+    if torch.cuda.is_available():
+        try:
+            return t.pin_memory()
+        except RuntimeError:
+            pass
+    return t
+
+
+def _storage_dtype(data: np.ndarray):
+    """uint8 when the data is exactly {0,1}-valued (lossless; 4x less host->device traffic), else float32."""
+    if data.size and np.all((data == 0) | (data == 1)):
+        return np.uint8
+    return np.float32
+
+
+class Dataset:
+    """includes/utils.py:428-466.  ``data`` is (data, classes)."""
+
+    def __init__(self, data, batch_size=100, shuffle=True, compact=True):
+        data, classes = data
+        self.data = np.copy(data)
+        self.classes = np.copy(classes)
+        self.batch_size = batch_size
+        self.shuffle = shuffle
+        self.data_dim = self.data.shape[1]
+        self.epoch_len = int(math.ceil(len(self.data) / batch_size))
+        self.len = len(self.data)
+        self._host: Optional[torch.Tensor] = None
+        self._compact = compact
+        if shuffle:
+            self._permute()
+
+    def _permute(self):
+        indices = np.random.permutation(len(self.data))
+        self.data = self.data[indices]
+        self.classes = self.classes[indices]
+        self._host = None
+
+    def host_tensor(self) -> torch.Tensor:
+        """Pinned host copy in storage dtype (uint8 for binarised data)."""
+        if self._host is None:
+            dt = _storage_dtype(self.data) if self._compact else np.float32
+            self._host = _pinned(self.data, dt)
+        return self._host
+
+    def begin_epoch(self):
+        """Reshuffle like get_batches does at the start of every epoch (utils.py:450-454)."""
+        if self.shuffle:
+            self._permute()
+
+    def get_batches(self):
+        self.begin_epoch()
+        for i in range(0, len(self.data), self.batch_size):
+            yield self.data[i: i + self.batch_size]
+
+    def __len__(self):
+        return self.epoch_len
+
+
+class MEDataset:
+    """includes/utils.py:378-425.  ``data`` is (data, classes, labels)."""
+
+    def __init__(self, data, batch_size=100, shuffle=True):
+        self.data, self.classes, self.labels = [np.asarray(a) for a in data]
+        self.shuffle = shuffle
+        self.len = len(self.data)
+        assert len(self.labels) == self.len and len(self.classes) == self.len
+        self.batch_size = batch_size
+        self.epoch_len = int(math.ceil(len(self.data) / batch_size))
+        self.data_dim = self.data.shape[1]
+
+    def begin_epoch(self):
+        if self.shuffle:
+            indices = np.random.permutation(len(self.data))
+            self.data = self.data[indices]
+            self.labels = self.labels[indices]
+            self.classes = self.classes[indices]
+
+    def get_batches(self):
+        self.begin_epoch()
+        for i in range(0, len(self.data), self.batch_size):
+            s = slice(i, i + self.batch_size)
+            yield self.data[s], self.labels[s], self.classes[s]
+
+    def __len__(self):
+        return self.epoch_len
