@@ -36,7 +36,7 @@ class ReparamArgs(C.Structure):
                 ("mean", c_void_p), ("log_var", c_void_p), ("ld_zh", c_int64),
                 ("logits", c_void_p), ("ld_logits", c_int64),
                 ("eps_in", c_void_p), ("gumbel_in", c_void_p),
-                ("seed", c_uint64), ("step", c_uint64), ("row_offset", c_uint64),
+                ("seed", c_uint64), ("step", c_uint64), ("row_offset", c_uint64), ("step_dev", c_void_p),
                 ("tau", c_float),
                 ("Z_out", c_void_p), ("z_dtype", c_int32), ("ld_z", c_int64), ("z_cols", c_int32),
                 ("eps_out", c_void_p), ("zeta_out", c_void_p)]
@@ -53,7 +53,7 @@ class ElboArgs(C.Structure):
                 ("zeta", c_void_p), ("ld_zeta", c_int64),
                 ("tau", c_float),
                 ("prior_means", c_void_p), ("prior_log_vars", c_void_p),
-                ("kl_ratio", c_float), ("inv_global_batch", c_float), ("recon_scale", c_float),
+                ("kl_ratio", c_float), ("inv_global_batch", c_float), ("kl_ratio_dev", c_void_p), ("recon_scale", c_float),
                 ("per_sample", c_void_p), ("qc", c_void_p), ("argmax", c_void_p),
                 ("d_decoded", c_void_p), ("ld_ddec", c_int64), ("ddec_cols", c_int32),
                 ("d_mean_kl", c_void_p), ("d_log_var_kl", c_void_p), ("ld_dkl", c_int64),
@@ -99,12 +99,13 @@ SIGNATURES = {
     "dmvae_moe_fwd_bwd": (c_int, [c_void_p, C.POINTER(MoeArgs), c_void_p]),
     "dmvae_softmax_bwd_add": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int64, c_void_p, c_int, c_int64,
                                       c_int, c_int, c_void_p]),
-    "dmvae_adam": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float,
+    "dmvae_adam": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_void_p, c_float,
                            c_float, c_float, c_float, c_int, c_void_p]),
+    "dmvae_step_tick": (c_int, [c_void_p, c_void_p, c_float, c_float, c_float, c_void_p]),
     "dmvae_argmax_contingency": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_int, c_void_p,
                                          c_void_p, c_void_p]),
     "dmvae_dp_reduce_adam": (c_int, [c_void_p, c_int, c_int, C.POINTER(c_void_p), C.POINTER(c_void_p),
-                                     C.POINTER(c_void_p), c_void_p, c_void_p, c_int64, c_int64, c_int64, c_float,
+                                     C.POINTER(c_void_p), c_void_p, c_void_p, c_int64, c_int64, c_int64, c_float, c_void_p,
                                      c_float, c_float, c_float, c_void_p]),
     "dmvae_zero_f32": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "dmvae_cast_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),

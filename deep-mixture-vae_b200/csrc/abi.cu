@@ -155,8 +155,10 @@ __device__ __forceinline__ void adam_update4(float4& p, const float4 g, float4& 
 
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ params, float* __restrict__ grads,
                                                     float* __restrict__ m, float* __restrict__ v,
-                                                    __nv_bfloat16* __restrict__ pbf, int64_t n4, float lr_t, float b1,
-                                                    float b2, float eps, float gs, int zero_grads) {
+                                                    __nv_bfloat16* __restrict__ pbf, int64_t n4, float lr_t,
+                                                    const float* __restrict__ lr_t_dev, float b1, float b2, float eps,
+                                                    float gs, int zero_grads) {
+  if (lr_t_dev) lr_t = __ldg(lr_t_dev);
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (; i < n4; i += stride) {
@@ -178,8 +180,8 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ params, f
 }
 
 extern "C" int dmvae_adam(dmvae_ctx* ctx, float* params, float* grads, float* m, float* v, void* params_bf16, int64_t n,
-                          float lr_t, float beta1, float beta2, float eps, float grad_scale, int zero_grads,
-                          void* stream) {
+                          float lr_t, const float* lr_t_dev, float beta1, float beta2, float eps, float grad_scale,
+                          int zero_grads, void* stream) {
   DMVAE_CHECK_ARG(ctx && params && grads && m && v, "dmvae_adam: NULL pointer");
   DMVAE_CHECK_ARG(n >= 0 && n % 4 == 0, "dmvae_adam: n (%lld) must be a multiple of 4 (flat padded buffer)", (long long)n);
   DMVAE_CHECK_ARG((((uintptr_t)params | (uintptr_t)grads | (uintptr_t)m | (uintptr_t)v) & 15) == 0 &&
@@ -189,7 +191,28 @@ extern "C" int dmvae_adam(dmvae_ctx* ctx, float* params, float* grads, float* m,
   int64_t n4 = n / 4;
   int blocks = (int)min((int64_t)ctx->sm_count * 8, (n4 + 255) / 256);
   adam_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(params, grads, m, v, (__nv_bfloat16*)params_bf16, n4, lr_t,
-                                                         beta1, beta2, eps, grad_scale, zero_grads);
+                                                         lr_t_dev, beta1, beta2, eps, grad_scale, zero_grads);
+  DMVAE_LAUNCH_CHECK(ctx);
+  return DMVAE_OK;
+}
+
+// per-step device state for graph replay: {uint64 step; uint32 t; float lr_t}
+struct StepState {
+  unsigned long long step;
+  unsigned int t;
+  float lr_t;
+};
+__global__ void step_tick_kernel(StepState* st, float lr, float b1, float b2) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    st->step += 1ull;
+    unsigned int t = st->t + 1u;
+    st->t = t;
+    st->lr_t = (float)((double)lr * sqrt(1.0 - pow((double)b2, (double)t)) / (1.0 - pow((double)b1, (double)t)));
+  }
+}
+extern "C" int dmvae_step_tick(dmvae_ctx* ctx, void* state_dev, float lr, float beta1, float beta2, void* stream) {
+  DMVAE_CHECK_ARG(ctx && state_dev, "dmvae_step_tick: NULL argument");
+  step_tick_kernel<<<1, 32, 0, (cudaStream_t)stream>>>((StepState*)state_dev, lr, beta1, beta2);
   DMVAE_LAUNCH_CHECK(ctx);
   return DMVAE_OK;
 }
@@ -207,7 +230,9 @@ struct DpPeers {
 
 __global__ void __launch_bounds__(256) dp_reduce_adam_kernel(DpPeers peers, int rank, int world, float* __restrict__ m,
                                                               float* __restrict__ v, int64_t begin4, int64_t end4,
-                                                              float lr_t, float b1, float b2, float eps) {
+                                                              float lr_t, const float* __restrict__ lr_t_dev, float b1,
+                                                              float b2, float eps) {
+  if (lr_t_dev) lr_t = __ldg(lr_t_dev);
   int64_t i = begin4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (; i < end4; i += stride) {
@@ -235,8 +260,8 @@ __global__ void __launch_bounds__(256) dp_reduce_adam_kernel(DpPeers peers, int 
 
 extern "C" int dmvae_dp_reduce_adam(dmvae_ctx* ctx, int rank, int world, const float* const* grads_peers_host,
                                     float* const* params_peers_host, void* const* params_bf16_peers_host, float* m,
-                                    float* v, int64_t n, int64_t shard_begin, int64_t shard_end, float lr_t, float beta1,
-                                    float beta2, float eps, void* stream) {
+                                    float* v, int64_t n, int64_t shard_begin, int64_t shard_end, float lr_t,
+                                    const float* lr_t_dev, float beta1, float beta2, float eps, void* stream) {
   DMVAE_CHECK_ARG(ctx && grads_peers_host && params_peers_host && m && v, "dmvae_dp_reduce_adam: NULL pointer");
   DMVAE_CHECK_ARG(world >= 1 && world <= 8 && rank >= 0 && rank < world, "dmvae_dp_reduce_adam: world %d rank %d", world, rank);
   DMVAE_CHECK_ARG(shard_begin % 4 == 0 && shard_end % 4 == 0 && 0 <= shard_begin && shard_begin <= shard_end && shard_end <= n,
@@ -254,7 +279,7 @@ extern "C" int dmvae_dp_reduce_adam(dmvae_ctx* ctx, int rank, int world, const f
   int64_t n4 = (shard_end - shard_begin) / 4;
   int blocks = (int)min((int64_t)ctx->sm_count * 8, (n4 + 255) / 256);
   dp_reduce_adam_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(peers, rank, world, m, v, shard_begin / 4, shard_end / 4,
-                                                                   lr_t, beta1, beta2, eps);
+                                                                   lr_t, lr_t_dev, beta1, beta2, eps);
   DMVAE_LAUNCH_CHECK(ctx);
   return DMVAE_OK;
 }

@@ -15,7 +15,6 @@ namespace {
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
 constexpr int kMaxK = 128;                 // K values per lane <= 4
-constexpr int kKPL = kMaxK / 32;
 constexpr float kEps0 = 1e-20f;
 
 struct ElboParams {
@@ -48,7 +47,7 @@ __device__ __forceinline__ float recon8(const float (&x)[8], const float (&d)[8]
   return acc;
 }
 
-template <typename TX, typename TD, int INPUT>
+template <typename TX, typename TD, int INPUT, int kKPL>
 __global__ void __launch_bounds__(kThreads) elbo_kernel(const ElboParams p) {
   extern __shared__ float smem[];
   const dmvae_elbo_args& a = p.a;
@@ -82,11 +81,18 @@ __global__ void __launch_bounds__(kThreads) elbo_kernel(const ElboParams p) {
   }
   __syncthreads();
 
-  const float r = a.kl_ratio, s = a.inv_global_batch, s_rec = a.inv_global_batch * a.recon_scale;
+  const float r = a.kl_ratio_dev ? __ldg(a.kl_ratio_dev) : a.kl_ratio;
+  const float s = a.inv_global_batch, s_rec = a.inv_global_batch * a.recon_scale;
   const float logK = logf((float)K);
   const int warps_total = gridDim.x * kWarps;
 
   for (int row = blockIdx.x * kWarps + warp; row < a.rows; row += warps_total) {
+    // latent inputs first: their latency overlaps the streaming part
+    const float* mean = a.mean + (int64_t)row * a.ld_zh;
+    const float* lvp = a.log_var + (int64_t)row * a.ld_zh;
+    const float mu0 = lane < L ? __ldg(mean + lane) : 0.f, lv0 = lane < L ? __ldg(lvp + lane) : 0.f;
+    float logit0 = -INFINITY;
+    if (mode != DMVAE_MODE_VADE && lane < K) logit0 = __ldg(a.logits + (int64_t)row * a.ld_logits + lane);
     // =========================== reconstruction part (streams D) ===========================
     const TX* xr = reinterpret_cast<const TX*>(a.X) + (int64_t)row * a.ldx;
     const TD* dr = reinterpret_cast<const TD*>(a.decoded) + (int64_t)row * a.ld_dec;
@@ -124,11 +130,9 @@ __global__ void __launch_bounds__(kThreads) elbo_kernel(const ElboParams p) {
     const float R = warp_sum(racc);
 
     // =========================== latent part ===========================
-    const float* mean = a.mean + (int64_t)row * a.ld_zh;
-    const float* lvp = a.log_var + (int64_t)row * a.ld_zh;
     float sum_lv = 0.f;
     for (int l = lane; l < L; l += 32) {
-      float mu = mean[l], lv = lvp[l];
+      float mu = (l == lane) ? mu0 : mean[l], lv = (l == lane) ? lv0 : lvp[l];
       mu_s[l] = mu;
       elv_s[l] = expf(lv);
       sum_lv += lv;
@@ -162,7 +166,7 @@ __global__ void __launch_bounds__(kThreads) elbo_kernel(const ElboParams p) {
             }
           }
           A[jk] = sum_plv[k] - sum_lv - (float)L + acc;
-          sc[jk] = (mode == DMVAE_MODE_VADE) ? -0.5f * (zacc + sum_plv[k]) : a.logits[(int64_t)row * a.ld_logits + k];
+          sc[jk] = (mode == DMVAE_MODE_VADE) ? -0.5f * (zacc + sum_plv[k]) : (jk == 0 ? logit0 : a.logits[(int64_t)row * a.ld_logits + k]);
         }
       }
       // ---- softmax over K (warp shuffles), argmax (first maximum wins) ----
@@ -266,7 +270,7 @@ __global__ void __launch_bounds__(kThreads) elbo_kernel(const ElboParams p) {
         Gw[jk] = 0.f;
         zt[jk] = 0.f;
         if (k < K) {
-          sc[jk] = a.logits[(int64_t)row * a.ld_logits + k];
+          sc[jk] = jk == 0 ? logit0 : a.logits[(int64_t)row * a.ld_logits + k];
           zt[jk] = w_s[k];
           float acc = 0.f;
           for (int l = 0; l < L; ++l) acc += x1_s[l] * tab_m[k * Ls + l] + x2_s[l] * tab_b[k * Ls + l];
@@ -344,10 +348,10 @@ size_t elbo_smem_bytes(int L, int K, int Ls) {
   return sizeof(float) * (size_t)(2 * K * Ls + Kp + kWarps * (4 * Lp + 2 * Kp));
 }
 
-template <typename TX, typename TD, int INPUT>
-int launch_elbo(dmvae_ctx* ctx, const ElboParams& p, cudaStream_t st) {
+template <typename TX, typename TD, int INPUT, int KPL>
+int launch_elbo_k(dmvae_ctx* ctx, const ElboParams& p, cudaStream_t st) {
   const size_t smem = elbo_smem_bytes(p.a.L, p.a.K, p.Ls);
-  auto kern = elbo_kernel<TX, TD, INPUT>;
+  auto kern = elbo_kernel<TX, TD, INPUT, KPL>;
   if (smem > 48 * 1024) DMVAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 8;
   if (smem > 0) per_sm = (int)min((size_t)8, (size_t)(220 * 1024) / max(smem, (size_t)1));
@@ -356,6 +360,13 @@ int launch_elbo(dmvae_ctx* ctx, const ElboParams& p, cudaStream_t st) {
   kern<<<blocks, kThreads, smem, st>>>(p);
   DMVAE_LAUNCH_CHECK(ctx);
   return DMVAE_OK;
+}
+
+template <typename TX, typename TD, int INPUT>
+int launch_elbo(dmvae_ctx* ctx, const ElboParams& p, cudaStream_t st) {
+  if (p.a.K <= 32) return launch_elbo_k<TX, TD, INPUT, 1>(ctx, p, st);
+  if (p.a.K <= 64) return launch_elbo_k<TX, TD, INPUT, 2>(ctx, p, st);
+  return launch_elbo_k<TX, TD, INPUT, 4>(ctx, p, st);
 }
 
 int check_elbo_args(const dmvae_elbo_args* a) {
@@ -496,11 +507,12 @@ __global__ void __launch_bounds__(kRedThreads) elbo_reduce_final_kernel(const dm
   const int L = a.L, K = a.K, nF = 2 * L + 1;
   const int nsets = (a.mode == DMVAE_MODE_VADE) ? 2 : 1;
   const size_t set_stride = (size_t)G * (size_t)(K * nF);
-  const float s = a.inv_global_batch, r = a.kl_ratio;
+  const float s = a.inv_global_batch, r = a.kl_ratio_dev ? __ldg(a.kl_ratio_dev) : a.kl_ratio;
   int i = blockIdx.x * kRedThreads + threadIdx.x;
   if (i < K * L && d_means && d_log_vars) {
     int k = i / L, l = i - k * L;
     float U0 = 0.f, U1 = 0.f, Wk = 0.f, V0 = 0.f, V1 = 0.f, Dk = 0.f;
+#pragma unroll 8
     for (int g = 0; g < G; ++g) {
       const float* p0 = ws + (size_t)g * (K * nF) + (size_t)k * nF;
       U0 += p0[l]; U1 += p0[L + l]; Wk += p0[2 * L];
@@ -529,6 +541,7 @@ __global__ void __launch_bounds__(kRedThreads) elbo_reduce_final_kernel(const dm
   if (blockIdx.x == 0 && threadIdx.x < 4 && loss_out) {
     const float* lp = ws + (size_t)nsets * set_stride;
     float acc = 0.f;
+#pragma unroll 8
     for (int g = 0; g < G; ++g) acc += lp[g * 4 + threadIdx.x];
     loss_out[threadIdx.x] = s * acc;
   }

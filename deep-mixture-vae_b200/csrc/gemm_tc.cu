@@ -190,50 +190,112 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else {
     // ===================== epilogue =====================
+    // Each thread owns one output row and walks the tile in 32-column chunks straight out of TMEM.  All
+    // decisions (activation, mask, padding columns, store flavour) are warp-uniform and taken once per chunk;
+    // the per-element work of a pure data chunk is a max / select, a bf16 pack and 16-byte stores.
     mbar_wait(tmem_full_bar, 0);
     tcgen05_fence_after();
     const int q = warp & 3;                  // TMEM lane quarter this warp may access
     const int m = m0 + q * 32 + lane;
-    const bool first = blockIdx.z == 0;
+    const bool row_ok = m < M && nkb > 0;
+    const bool padded = ep.n_valid < ep.n_block;
+    int jb = padded ? (n0 % ep.n_block) : 0;  // column index inside the padding block (n_block % 32 == 0)
+    const __nv_bfloat16* mrow = ep.mask ? reinterpret_cast<const __nv_bfloat16*>(ep.mask) + (int64_t)m * ep.ld_mask : nullptr;
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
-      uint32_t v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-      if (m < M && nkb > 0) {
+      const int n = n0 + c0;
+      if (n >= N) break;
+      uint32_t raw[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, raw);
+      float v[32];
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const int n = n0 + c0 + g * 8;
-          if (n >= N) break;
-          float o[8], mk[8];
-          if (ep.mask && n + 8 <= N) {
-            Vec8<__nv_bfloat16>::load(reinterpret_cast<const __nv_bfloat16*>(ep.mask) + (int64_t)m * ep.ld_mask + n, mk);
-          } else {
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+      const int ncols = min(32, N - n);
+      if (row_ok) {
+        if (ep.bias && blockIdx.z == 0) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-              mk[j] = (ep.mask && n + j < N)
-                          ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(ep.mask)[(int64_t)m * ep.ld_mask + n + j])
-                          : 1.f;
-          }
+          for (int j = 0; j < 32; ++j)
+            if (j < ncols) v[j] += __ldg(ep.bias + n + j);
+        }
+        if (ep.act == DMVAE_ACT_RELU) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) o[j] = epi_apply(ep, n + j, __uint_as_float(v[g * 8 + j]), mk[j], first);
-          if (ep.out_dtype == DMVAE_BF16) {
-            __nv_bfloat16* c = reinterpret_cast<__nv_bfloat16*>(C) + (int64_t)m * ldc + n;
-            if (n + 8 <= N) Vec8<__nv_bfloat16>::store(c, o);
-            else
-              for (int j = 0; n + j < N; ++j) c[j] = __float2bfloat16_rn(o[j]);
-          } else {
-            float* c = reinterpret_cast<float*>(C) + (int64_t)m * ldc + n;
-            if (ep.accumulate == 2) {
-              for (int j = 0; j < 8 && n + j < N; ++j) atomicAdd(c + j, o[j]);
-            } else if (ep.accumulate == 1) {
-              for (int j = 0; j < 8 && n + j < N; ++j) c[j] += o[j];
-            } else if (n + 8 <= N) {
-              Vec8<float>::store(c, o);
-            } else {
-              for (int j = 0; n + j < N; ++j) c[j] = o[j];
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
+        if (mrow) {
+          if (ncols == 32) {
+#pragma unroll
+            for (int g4 = 0; g4 < 4; ++g4) {
+              const uint4 w = __ldg(reinterpret_cast<const uint4*>(mrow + n) + g4);
+              const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                // bf16 > 0  <=>  sign bit clear and magnitude non-zero
+                const uint32_t lo = ww[i] & 0xffffu, hi = ww[i] >> 16;
+                v[g4 * 8 + 2 * i] = (lo - 1u < 0x7fffu) ? v[g4 * 8 + 2 * i] : 0.f;
+                v[g4 * 8 + 2 * i + 1] = (hi - 1u < 0x7fffu) ? v[g4 * 8 + 2 * i + 1] : 0.f;
+              }
             }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < ncols) v[j] = __bfloat162float(mrow[n + j]) > 0.f ? v[j] : 0.f;
           }
         }
+        if (padded && jb + 32 > ep.n_valid) {          // the chunk touches the ones / zero padding columns
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int t = jb + j;
+            v[j] = t < ep.n_valid ? v[j] : (t == ep.n_valid ? ep.pad_one : 0.f);
+          }
+        }
+        if (ep.out_dtype == DMVAE_BF16) {
+          __nv_bfloat16* c = reinterpret_cast<__nv_bfloat16*>(C) + (int64_t)m * ldc + n;
+          if (ncols == 32) {
+#pragma unroll
+            for (int g4 = 0; g4 < 4; ++g4) {
+              uint32_t pk[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                __nv_bfloat162 h = __floats2bfloat162_rn(v[g4 * 8 + 2 * i], v[g4 * 8 + 2 * i + 1]);
+                pk[i] = *reinterpret_cast<uint32_t*>(&h);
+              }
+              reinterpret_cast<uint4*>(c)[g4] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < ncols) c[j] = __float2bfloat16_rn(v[j]);
+          }
+        } else {
+          float* c = reinterpret_cast<float*>(C) + (int64_t)m * ldc + n;
+          if (ncols == 32) {
+#pragma unroll
+            for (int g8 = 0; g8 < 8; ++g8) {
+              float4 o = make_float4(v[g8 * 4], v[g8 * 4 + 1], v[g8 * 4 + 2], v[g8 * 4 + 3]);
+              float4* cp = reinterpret_cast<float4*>(c) + g8;
+              if (ep.accumulate == 2) {
+                atomicAdd(cp, o);                          // split-K: vector fp32 reduction in L2
+              } else if (ep.accumulate == 1) {
+                float4 old = *cp;
+                *cp = make_float4(old.x + o.x, old.y + o.y, old.z + o.z, old.w + o.w);
+              } else {
+                *cp = o;
+              }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < ncols) {
+                if (ep.accumulate == 2) atomicAdd(c + j, v[j]);
+                else if (ep.accumulate == 1) c[j] += v[j];
+                else c[j] = v[j];
+              }
+          }
+        }
+      }
+      if (padded) {
+        jb += 32;
+        if (jb >= ep.n_block) jb -= ep.n_block;
       }
     }
   }
@@ -320,7 +382,7 @@ int dispatch_bn(dmvae_ctx* ctx, const void* A, int64_t lda, const void* B, int64
   const int mt = (M + BM - 1) / BM;
   int bn = 64;
   if (N > 64) bn = 128;
-  if (N >= 256 && (long long)mt * ((N + 255) / 256) * split >= 2LL * ctx->sm_count) bn = 256;
+  (void)mt;   // 128x256 tiles (one CTA per SM) need the persistent / double-buffered-TMEM variant to pay off
   CUtensorMap ta, tb;
   int rc;
   // A: K-major -> stored [M, K] (inner K); MN-major -> stored [K, M] (inner M)
@@ -350,6 +412,7 @@ int dmvae_gemm_bf16_tc(dmvae_ctx* ctx, int trans_a, int trans_b, const void* A, 
   DMVAE_CHECK_ARG(((uintptr_t)C & 15) == 0, "gemm(bf16): C must be 16-byte aligned");
   if (epi->relu_mask) DMVAE_CHECK_ARG(epi->ld_mask % 8 == 0 && ((uintptr_t)epi->relu_mask & 15) == 0, "gemm(bf16): mask must be 16-byte aligned with ld % 8 == 0");
   EpiParams ep = make_epi_params(*epi, DMVAE_BF16);
+  DMVAE_CHECK_ARG(epi->n_valid >= epi->n_block || epi->n_block % 32 == 0, "gemm(bf16): n_block (%d) must be a multiple of 32", epi->n_block);
   const int split = epi->split_k;
   // op(A) [M,K]: trans_a=0 -> stored [M,K] = K-major; trans_a=1 -> stored [K,M] = MN-major
   // op(B) [K,N]: trans_b=0 -> stored [K,N] = MN-major; trans_b=1 -> stored [N,K] = K-major

@@ -36,6 +36,7 @@ __global__ void __launch_bounds__(256) reparam_fwd_kernel(const dmvae_reparam_ar
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
   const int L = a.L, K = a.K;
   const uint2 key = make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+  const uint32_t step = (uint32_t)(a.step_dev ? *a.step_dev : a.step);
   for (int row = warp; row < a.rows; row += nwarps) {
     const uint32_t grow = (uint32_t)(a.row_offset + (uint64_t)row);
     const float* mean = a.mean + (int64_t)row * a.ld_zh;
@@ -48,7 +49,7 @@ __global__ void __launch_bounds__(256) reparam_fwd_kernel(const dmvae_reparam_ar
 #pragma unroll
         for (int i = 0; i < 4; ++i) e[i] = (4 * j + i < L) ? a.eps_in[(int64_t)row * L + 4 * j + i] : 0.f;
       } else {
-        uint4 x = philox4x32_10(make_uint4(grow, (uint32_t)j, (uint32_t)a.step, 0u), key);
+        uint4 x = philox4x32_10(make_uint4(grow, (uint32_t)j, step, 0u), key);
         box_muller(x.x, x.y, e[0], e[1]);
         box_muller(x.z, x.w, e[2], e[3]);
       }
@@ -76,7 +77,7 @@ __global__ void __launch_bounds__(256) reparam_fwd_kernel(const dmvae_reparam_ar
           float g;
           if (a.gumbel_in) g = a.gumbel_in[(int64_t)row * K + k];
           else {
-            uint4 x = philox4x32_10(make_uint4(grow, (uint32_t)(k >> 2), (uint32_t)a.step, 1u), key);
+            uint4 x = philox4x32_10(make_uint4(grow, (uint32_t)(k >> 2), step, 1u), key);
             uint32_t xs = (k & 3) == 0 ? x.x : (k & 3) == 1 ? x.y : (k & 3) == 2 ? x.z : x.w;
             g = -logf(1e-20f - logf(u01(xs) + 1e-20f));                  // utils.py:17-19
           }

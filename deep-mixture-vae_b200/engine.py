@@ -69,10 +69,22 @@ class AdamState:
         self.v = torch.zeros(n, dtype=torch.float32, device=device)
         self.t = 0
         self.lr, self.beta1, self.beta2, self.eps = lr, beta1, beta2, eps
+        # device-resident {uint64 step; uint32 t; float lr_t} read by the kernels under CUDA-graph replay
+        self.state_dev = torch.zeros(4, dtype=torch.int32, device=device)
+        self.state_valid = False
 
     def next_lr_t(self) -> float:
         self.t += 1
+        self.state_valid = False
         return self.lr * math.sqrt(1.0 - self.beta2 ** self.t) / (1.0 - self.beta1 ** self.t)
+
+    def upload_state(self, step_count: int):
+        """device step = step_count - 1 and t = self.t: the graph's first node (dmvae_step_tick) increments both."""
+        st = np.zeros(1, dtype=[("step", "<u8"), ("t", "<u4"), ("lr_t", "<f4")])
+        st["step"] = (step_count - 1) & 0xFFFFFFFFFFFFFFFF
+        st["t"] = self.t
+        self.state_dev.copy_(torch.from_numpy(st.view(np.int32).copy()), non_blocking=False)
+        self.state_valid = True
 
 
 class Engine:
@@ -363,17 +375,40 @@ class Engine:
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
+    # CUDA-event timers on the launching stream (bench.py): timers = {"elbo": [], "gemm": [] ...}
+    timers = None
+
+    def _tic(self, key):
+        if self.timers is None or key not in self.timers:
+            return None
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record(torch.cuda.current_stream(self.device))
+        return ev
+
+    def _toc(self, key, start):
+        if start is None:
+            return
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record(torch.cuda.current_stream(self.device))
+        self.timers[key].append((start, ev))
+
+    def timer_ms(self, key):
+        """Per-launch durations (ms) of the recorded event pairs; call after a synchronize."""
+        return [a.elapsed_time(b) for a, b in self.timers.get(key, [])]
+
     # ------------------------------------------------------------------------------------------
     # kernel wrappers
     # ------------------------------------------------------------------------------------------
     def _fwd(self, name, A, lda, Y, out_dt, act, rows, W=None, ldw=None, n_out=None, n_in_pad=None):
         ly = self.layers[name]
         Wt = self.W(name, op=True) if W is None else W
+        t0 = self._tic("gemm")
         _abi.check(self.lib.dmvae_linear_fwd(self.ctx, self.dt, A.data_ptr(), lda, Wt.data_ptr(),
                                              ly.out_pad if ldw is None else ldw, Y.data_ptr(), Y.stride(0), out_dt, rows,
                                              ly.out_pad if n_out is None else n_out,
                                              ly.in_pad if n_in_pad is None else n_in_pad, act, ly.n_valid, ly.n_block,
                                              self._stream()))
+        self._toc("gemm", t0)
 
     def _wgrad(self, name, A, lda, dY, lddy, rows, n_out=None, col0=0, accumulate=None):
         ly = self.layers[name]
@@ -383,9 +418,11 @@ class Engine:
         acc = 1 if sk > 1 else 0
         if accumulate is not None:
             acc = accumulate
+        t0 = self._tic("gemm")
         _abi.check(self.lib.dmvae_linear_wgrad(self.ctx, self.dt, A.data_ptr(), lda, dY.data_ptr(), lddy,
                                                dW.data_ptr() + 4 * col0, ly.out_pad, rows, ly.in_pad, n_out, acc, sk,
                                                self._stream()))
+        self._toc("gemm", t0)
 
     def _pick_split_k(self, rows, m, n) -> int:
         if self.dt != BF16:
@@ -402,6 +439,7 @@ class Engine:
                n_in_pad=None, n_out_pad=None):
         ly = self.layers[name]
         Wt = self.W(name, op=True) if W is None else W
+        t0 = self._tic("gemm")
         _abi.check(self.lib.dmvae_linear_dgrad(self.ctx, self.dt, dY.data_ptr(), lddy, Wt.data_ptr(),
                                                ly.out_pad if ldw is None else ldw,
                                                act_in.data_ptr() if act_in is not None else None, ld_act,
@@ -409,6 +447,7 @@ class Engine:
                                                ly.in_pad if n_in_pad is None else n_in_pad,
                                                ly.out_pad if n_out_pad is None else n_out_pad, prev_valid, prev_block,
                                                self._stream()))
+        self._toc("gemm", t0)
 
     # ------------------------------------------------------------------------------------------
     # input staging
@@ -440,8 +479,10 @@ class Engine:
         else:
             self._fwd("zh", a, a.stride(0), self.zh, F32, _abi.ACT_NONE, rows)
 
-    def reparam(self, rows: int, eps_injected: bool, gumbel_injected: bool, row_offset: int = 0, step: Optional[int] = None):
+    def reparam(self, rows: int, eps_injected: bool, gumbel_injected: bool, row_offset: int = 0, step: Optional[int] = None,
+                step_dev: Optional[int] = None):
         ra = _abi.ReparamArgs()
+        ra.step_dev = step_dev
         ra.rows, ra.L, ra.K = rows, self.L, self.K
         ra.mean = self.zh.data_ptr()
         ra.log_var = self.zh.data_ptr() + 4 * self.L
@@ -465,8 +506,9 @@ class Engine:
             a = self.act[nm]
         self._fwd("decx", a, a.stride(0), self.decoded, self.dec_dt, _abi.ACT_NONE, rows)
 
-    def _elbo_args(self, X, xdt, rows, kl_ratio, inv_global_batch, recon_scale=1.0) -> _abi.ElboArgs:
+    def _elbo_args(self, X, xdt, rows, kl_ratio, inv_global_batch, recon_scale=1.0, klr_dev=None) -> _abi.ElboArgs:
         ea = _abi.ElboArgs()
+        ea.kl_ratio_dev = klr_dev
         ea.mode = _abi.MODE_VADE if self.model == "vade" else (
             _abi.MODE_DMVAE_SAMPLED if self.cluster_sample else _abi.MODE_DMVAE)
         ea.input_type = _abi.INPUT_BINARY if self.input_type == "binary" else _abi.INPUT_REAL
@@ -491,12 +533,14 @@ class Engine:
         ea.w_scratch, ea.f_scratch = self.w_scratch.data_ptr(), self.f_scratch.data_ptr()
         return ea
 
-    def elbo(self, X, xdt, rows, kl_ratio=1.0, inv_global_batch=None, recon_scale=1.0, prior_grads=True):
+    def elbo(self, X, xdt, rows, kl_ratio=1.0, inv_global_batch=None, recon_scale=1.0, prior_grads=True, klr_dev=None):
         """Fused ELBO forward + backward and its cross-sample reductions."""
         s = (1.0 / rows) if inv_global_batch is None else inv_global_batch
-        ea = self._elbo_args(X, xdt, rows, kl_ratio, s, recon_scale)
+        ea = self._elbo_args(X, xdt, rows, kl_ratio, s, recon_scale, klr_dev)
         st = self._stream()
+        t0 = self._tic("elbo")
         _abi.check(self.lib.dmvae_elbo_fwd_bwd(self.ctx, C.byref(ea), st))
+        self._toc("elbo", t0)
         gm = self.table("means", grad=True).data_ptr() if prior_grads else None
         gl = self.table("log_vars", grad=True).data_ptr() if prior_grads else None
         _abi.check(self.lib.dmvae_elbo_reduce(self.ctx, C.byref(ea), gm, gl, 0, self.loss_out.data_ptr(),
@@ -602,12 +646,14 @@ class Engine:
         _abi.check(self.lib.dmvae_zero_f32(self.ctx, self.grads.data_ptr(), self.n_params, self._stream()))
         self._grads_dirty = False
 
-    def adam(self, opt: AdamState, zero_grads: bool = True):
-        lr_t = opt.next_lr_t()
+    def adam(self, opt: AdamState, zero_grads: bool = True, use_dev: bool = False):
+        lr_t = 0.0 if use_dev else opt.next_lr_t()
+        t0 = self._tic("adam")
         _abi.check(self.lib.dmvae_adam(self.ctx, self.params.data_ptr(), self.grads.data_ptr(), opt.m.data_ptr(),
                                        opt.v.data_ptr(), self.params_op.data_ptr() if self.params_op is not None else None,
-                                       self.n_params, lr_t, opt.beta1, opt.beta2, opt.eps, 1.0, 1 if zero_grads else 0,
-                                       self._stream()))
+                                       self.n_params, lr_t, (opt.state_dev.data_ptr() + 12) if use_dev else None,
+                                       opt.beta1, opt.beta2, opt.eps, 1.0, 1 if zero_grads else 0, self._stream()))
+        self._toc("adam", t0)
         if zero_grads:
             self._grads_dirty = False
 
@@ -616,34 +662,88 @@ class Engine:
     # ------------------------------------------------------------------------------------------
     def forward_backward(self, X: torch.Tensor, rows: int, eps: Optional[torch.Tensor] = None,
                          gumbel: Optional[torch.Tensor] = None, kl_ratio: float = 1.0, inv_global_batch=None,
-                         row_offset: int = 0, recon_scale: float = 1.0, backward: bool = True, mode: str = "all"):
-        """encoder -> reparam -> decoder -> fused ELBO (-> gradient GEMMs).  Results stay on the device."""
-        if rows > self.max_rows:
-            self._alloc_activations(rows)
-        if getattr(self, "_params_dirty", False):
-            self.sync_operand_copy()
-        if backward and getattr(self, "_grads_dirty", False):
-            self.zero_grads()                      # split-K wgrads accumulate into the gradient buffer
-        if eps is not None:
-            self.eps_in[:rows].copy_(eps.reshape(rows, self.L))
-        if gumbel is not None:
-            self.gumbel_in[:rows].copy_(gumbel.reshape(rows, self.K))
+                         row_offset: int = 0, recon_scale: float = 1.0, backward: bool = True, mode: str = "all",
+                         dev_state: Optional[AdamState] = None):
+        """encoder -> reparam -> decoder -> fused ELBO (-> gradient GEMMs).  Results stay on the device.
+        dev_state: read the Philox step / kl_ratio from device memory (CUDA-graph capture)."""
+        if dev_state is None:
+            if rows > self.max_rows:
+                self._alloc_activations(rows)
+            if getattr(self, "_params_dirty", False):
+                self.sync_operand_copy()
+            if backward and getattr(self, "_grads_dirty", False):
+                self.zero_grads()                  # split-K wgrads accumulate into the gradient buffer
+            if eps is not None:
+                self.eps_in[:rows].copy_(eps.reshape(rows, self.L))
+            if gumbel is not None:
+                self.gumbel_in[:rows].copy_(gumbel.reshape(rows, self.K))
         X, xdt = self.stage_input(X, rows)
         self.encode(rows)
-        self.reparam(rows, eps is not None, gumbel is not None, row_offset)
+        self.reparam(rows, eps is not None, gumbel is not None, row_offset,
+                     step_dev=dev_state.state_dev.data_ptr() if dev_state is not None else None)
         self.decode(rows)
         flags = dict(all=(True, True, True, True), vae=(True, True, False, True), prior=(False, False, True, False))[mode]
-        self.elbo(X, xdt, rows, kl_ratio, inv_global_batch, recon_scale, prior_grads=(mode == "all"))
+        klr_dev = self.klr_dev.data_ptr() if (dev_state is not None and mode == "all") else None
+        self.elbo(X, xdt, rows, kl_ratio, inv_global_batch, recon_scale, prior_grads=(mode == "all"), klr_dev=klr_dev)
         if backward:
             self.backward(rows, train_decoder=flags[0], train_z=flags[1], train_c=flags[2], train_trunk=flags[3])
             self._grads_dirty = True
 
+    use_graphs = True
+
     def train_step(self, X: torch.Tensor, rows: int, opt: AdamState, eps=None, gumbel=None, kl_ratio=1.0,
-                   mode: str = "all", recon_scale: float = 1.0):
-        """One optimisation step (VAE.train_op body, base_models.py:117-129).  Returns nothing; read loss_out."""
+                   mode: str = "all", recon_scale: float = 1.0, graph: Optional[bool] = None):
+        """One optimisation step (VAE.train_op body, base_models.py:117-129).  Returns nothing; read loss_out.
+        Without injected noise the step is captured once per (input buffer, rows, mode, optimiser) into a CUDA graph
+        and replayed: per-step scalars (Adam's lr_t, the Philox step, kl_ratio) live in device memory."""
+        use_graph = self.use_graphs if graph is None else graph
+        if use_graph and eps is None and gumbel is None and self.world == 1:
+            return self._train_step_graph(X, rows, opt, kl_ratio, mode, recon_scale)
         self.forward_backward(X, rows, eps, gumbel, kl_ratio, None, 0, recon_scale, True, mode)
         self.adam(opt, zero_grads=True)
         self.step_count += 1
+
+    def _train_step_graph(self, X, rows, opt, kl_ratio, mode, recon_scale):
+        if not hasattr(self, "_graphs"):
+            self._graphs = {}
+            self._graph_replay_launches = 0
+            self.klr_dev = torch.ones(1, dtype=torch.float32, device=self.device)
+            self._klr_host = 1.0
+        key = (X.data_ptr(), X.dtype, X.stride(0), rows, mode, id(opt), float(recon_scale),
+               float(kl_ratio) if mode != "all" else None)
+        ent = self._graphs.get(key)
+        if ent is None:
+            # first use of this signature: one eager step (also warms the TMA-descriptor cache and the kernels'
+            # shared-memory attributes), then capture the same sequence for every later step
+            self.forward_backward(X, rows, None, None, kl_ratio, None, 0, recon_scale, True, mode)
+            self.adam(opt, zero_grads=True)
+            self.step_count += 1
+            torch.cuda.current_stream(self.device).synchronize()
+            g = torch.cuda.CUDAGraph()
+            l0 = int(self.lib.dmvae_ctx_launch_count(self.ctx))
+            with torch.cuda.graph(g):
+                _abi.check(self.lib.dmvae_step_tick(self.ctx, opt.state_dev.data_ptr(), opt.lr, opt.beta1, opt.beta2,
+                                                    self._stream()))
+                self.forward_backward(X, rows, None, None, kl_ratio, None, 0, recon_scale, True, mode, dev_state=opt)
+                self.adam(opt, zero_grads=True, use_dev=True)
+            n_nodes = int(self.lib.dmvae_ctx_launch_count(self.ctx)) - l0
+            self._graphs[key] = (g, n_nodes)
+            self._grads_dirty = False
+            return
+        g, n_nodes = ent
+        if getattr(self, "_params_dirty", False):
+            self.sync_operand_copy()
+        if getattr(self, "_grads_dirty", False):
+            self.zero_grads()
+        if not opt.state_valid:
+            opt.upload_state(self.step_count)
+        if mode == "all" and kl_ratio != self._klr_host:
+            self.klr_dev.fill_(float(kl_ratio))
+            self._klr_host = float(kl_ratio)
+        g.replay()
+        opt.t += 1                     # host mirrors of the device counters
+        self.step_count += 1
+        self._graph_replay_launches += n_nodes
 
     def run_epoch(self, host: torch.Tensor, batch_size: int, opt: AdamState, kl_ratio: float = 1.0, mode: str = "all",
                   max_steps: Optional[int] = None) -> float:
@@ -692,7 +792,8 @@ class Engine:
         return float(self._loss_host[:nb, col].sum()) / nb
 
     def launches(self) -> int:
-        return int(self.lib.dmvae_ctx_launch_count(self.ctx))
+        """Kernels launched so far: direct launches counted by the library + nodes of replayed CUDA graphs."""
+        return int(self.lib.dmvae_ctx_launch_count(self.ctx)) + getattr(self, "_graph_replay_launches", 0)
 
     def close(self):
         if getattr(self, "ctx", None):

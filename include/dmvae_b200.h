@@ -114,6 +114,7 @@ typedef struct dmvae_reparam_args {
   const float* eps_in;                                       /* injected N(0,1) [rows, L] (ld = L) or NULL -> Philox */
   const float* gumbel_in;                                    /* injected Gumbel [rows, K] (ld = K) or NULL -> Philox */
   uint64_t seed; uint64_t step; uint64_t row_offset;         /* Philox key / counter; row_offset = global row of row 0 */
+  const uint64_t* step_dev;                                   /* optional device-resident step counter (overrides step; CUDA-graph replay) */
   float tau;                                                  /* concrete temperature */
   void* Z_out; int32_t z_dtype; int64_t ld_z; int32_t z_cols; /* Z in operand dtype, [rows, ld_z]; ones column at L, zeros to z_cols */
   float* eps_out;                                             /* fp32 [rows, L]: the eps actually used (kept for the backward) */
@@ -147,6 +148,7 @@ typedef struct dmvae_elbo_args {
   float tau;
   const float* prior_means; const float* prior_log_vars;       /* fp32 [K,L] dense */
   float kl_ratio; float inv_global_batch;
+  const float* kl_ratio_dev;                                   /* optional device-resident kl_ratio (overrides kl_ratio; CUDA-graph replay) */
   float recon_scale;       /* weight of the reconstruction term in the loss and its gradient (1; 0 for prior pre-training) */
   /* outputs */
   float* per_sample;       /* [rows,4]: recon, KL_c, KL_z, recon_scale recon + kl_ratio (KL_c + KL_z) */
@@ -192,8 +194,11 @@ int dmvae_softmax_bwd_add(dmvae_ctx* ctx, int rows, int K, const float* q, const
  * theta -= lr_t m/(sqrt(v)+eps), lr_t = lr sqrt(1-b2^t)/(1-b1^t) computed by the caller in double.
  * Flat over n fp32 parameters.  Optionally writes the bf16 operand copy and clears the gradient. */
 int dmvae_adam(dmvae_ctx* ctx, float* params, float* grads, float* m, float* v, void* params_bf16 /* or NULL */,
-               int64_t n, float lr_t, float beta1, float beta2, float eps, float grad_scale,
-               int zero_grads, void* stream);
+               int64_t n, float lr_t, const float* lr_t_dev /* optional device scalar overriding lr_t */,
+               float beta1, float beta2, float eps, float grad_scale, int zero_grads, void* stream);
+/* Per-step device state for CUDA-graph replay: state = {uint64 step; uint32 t; float lr_t}.  One tiny kernel:
+ * step += 1, t += 1, lr_t = lr sqrt(1-beta2^t)/(1-beta1^t) (double precision). */
+int dmvae_step_tick(dmvae_ctx* ctx, void* state_dev, float lr, float beta1, float beta2, void* stream);
 
 /* ---- evaluation helpers (get_accuracy, base_models.py:425-432; utils.py:22-34) -------------- */
 /* argmax over K of fp32 [rows,K] and contingency counts d[cluster, class] += 1 (int32 [K, n_labels]) */
@@ -206,7 +211,7 @@ int dmvae_argmax_contingency(dmvae_ctx* ctx, const float* scores, int64_t ld, in
 int dmvae_dp_reduce_adam(dmvae_ctx* ctx, int rank, int world, const float* const* grads_peers_host,
                          float* const* params_peers_host, void* const* params_bf16_peers_host,
                          float* m, float* v, int64_t n, int64_t shard_begin, int64_t shard_end,
-                         float lr_t, float beta1, float beta2, float eps, void* stream);
+                         float lr_t, const float* lr_t_dev, float beta1, float beta2, float eps, void* stream);
 /* zero a fp32 buffer (gradient accumulators) */
 int dmvae_zero_f32(dmvae_ctx* ctx, float* p, int64_t n, void* stream);
 /* fp32 -> bf16 copy (operand copy of the parameters) */

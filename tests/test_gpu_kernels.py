@@ -392,7 +392,7 @@ def test_adam_tf_semantics(lib, ctx):
     for t in range(1, 4):
         lr_t = 0.002 * math.sqrt(1 - 0.999 ** t) / (1 - 0.9 ** t)
         gr.copy_(dev(g))
-        _abi.check(lib.dmvae_adam(ctx, p.data_ptr(), gr.data_ptr(), m.data_ptr(), v.data_ptr(), pb.data_ptr(), n, lr_t, 0.9,
+        _abi.check(lib.dmvae_adam(ctx, p.data_ptr(), gr.data_ptr(), m.data_ptr(), v.data_ptr(), pb.data_ptr(), n, lr_t, None, 0.9,
                                   0.999, 1e-8, 1.0, 1, stream()))
         rg.adam_tf_step(th64, g.astype(np.float64), m64, v64, t, 0.002)
     torch.cuda.synchronize()
@@ -400,6 +400,27 @@ def test_adam_tf_semantics(lib, ctx):
     assert np.all(gr.cpu().numpy() == 0)
     assert np.array_equal(pb.float().cpu().numpy(), p.to(torch.bfloat16).float().cpu().numpy())
     assert np.all(p.cpu().numpy()[::7] == th[::7])          # zero gradient from the start -> never moves
+
+
+def test_step_tick_and_device_lr(lib, ctx):
+    """CUDA-graph replay reads Adam's lr_t and the Philox step from device memory."""
+    from dmvae_b200 import _abi
+    st = np.zeros(1, dtype=[("step", "<u8"), ("t", "<u4"), ("lr_t", "<f4")])
+    st["step"], st["t"] = 41, 6
+    sd = torch.from_numpy(st.view(np.int32).copy()).cuda()
+    _abi.check(lib.dmvae_step_tick(ctx, sd.data_ptr(), 0.002, 0.9, 0.999, stream()))
+    torch.cuda.synchronize()
+    back = sd.cpu().numpy().view(st.dtype)
+    assert back["step"][0] == 42 and back["t"][0] == 7
+    assert abs(back["lr_t"][0] - 0.002 * math.sqrt(1 - 0.999 ** 7) / (1 - 0.9 ** 7)) < 1e-8 * 0.002 * 50
+    n = 1024
+    p, g = torch.ones(n, device="cuda"), torch.ones(n, device="cuda")
+    m, v = torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    _abi.check(lib.dmvae_adam(ctx, p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), None, n, 123.0,
+                              sd.data_ptr() + 12, 0.9, 0.999, 1e-8, 1.0, 0, stream()))
+    torch.cuda.synchronize()
+    exp = 1.0 - float(back["lr_t"][0]) * 0.1 / (math.sqrt(0.001) + 1e-8)
+    assert abs(float(p[0]) - exp) < 1e-6
 
 
 def test_stage_input_and_argmax(lib, ctx):
