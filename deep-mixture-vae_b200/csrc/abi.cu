@@ -96,15 +96,25 @@ extern "C" int dmvae_cast_bf16(dmvae_ctx* ctx, const float* src, void* dst, int6
 // ---------------------------------------------------------------------------------------------
 template <typename TX, typename TO>
 __global__ void stage_input_kernel(const TX* __restrict__ X, int64_t ldx, TO* __restrict__ A, int64_t lda, int rows,
-                                   int D) {
-  // one warp per row, lanes stride over the padded width
+                                   int D, int vec) {
+  // one warp per row; 8 elements per lane per iteration when the row pitches allow vector access
   int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
   int nwarps = (gridDim.x * blockDim.x) >> 5;
   for (int r = warp; r < rows; r += nwarps) {
     const TX* x = X + (int64_t)r * ldx;
     TO* a = A + (int64_t)r * lda;
-    for (int j = lane; j < (int)lda; j += 32) {
+    int j0 = 0;
+    if (vec) {
+      const int Dv = D & ~7;
+      for (int j = lane * 8; j < Dv; j += 256) {
+        float v[8];
+        Vec8<TX>::load(x + j, v);
+        Vec8<TO>::store(a + j, v);
+      }
+      j0 = Dv;
+    }
+    for (int j = j0 + lane; j < (int)lda; j += 32) {
       float v = j < D ? to_f32<TX>(x[j]) : (j == D ? 1.f : 0.f);
       a[j] = from_f32<TO>(v);
     }
@@ -118,7 +128,9 @@ extern "C" int dmvae_stage_input(dmvae_ctx* ctx, const void* X, int x_dtype, int
   if (rows == 0) return DMVAE_OK;
   int blocks = min(ctx->sm_count * 8, (rows + 7) / 8);
   cudaStream_t s = (cudaStream_t)stream;
-#define STAGE(TX, TO) stage_input_kernel<TX, TO><<<blocks, 256, 0, s>>>((const TX*)X, ldx, (TO*)A0, ld_out, rows, D)
+  const int vec = (ldx % 8 == 0) && (ld_out % 8 == 0) && (((uintptr_t)X) % (8 * dmvae_dtype_size(x_dtype)) == 0) &&
+                  (((uintptr_t)A0) % (8 * dmvae_dtype_size(out_dtype)) == 0);
+#define STAGE(TX, TO) stage_input_kernel<TX, TO><<<blocks, 256, 0, s>>>((const TX*)X, ldx, (TO*)A0, ld_out, rows, D, vec)
   if (x_dtype == DMVAE_F32 && out_dtype == DMVAE_F32) STAGE(float, float);
   else if (x_dtype == DMVAE_F32 && out_dtype == DMVAE_BF16) STAGE(float, __nv_bfloat16);
   else if (x_dtype == DMVAE_U8 && out_dtype == DMVAE_F32) STAGE(uint8_t, float);

@@ -381,7 +381,8 @@ int dispatch_bn(dmvae_ctx* ctx, const void* A, int64_t lda, const void* B, int64
   // tile width: the widest that still gives every SM work
   const int mt = (M + BM - 1) / BM;
   int bn = 64;
-  if (N > 64) bn = 128;
+  // 128-wide tiles unless they would leave SMs idle (two CTAs fit per SM): then 64-wide tiles double the CTA count
+  if (N > 64 && (long long)mt * ((N + 127) / 128) * split >= (long long)ctx->sm_count) bn = 128;
   (void)mt;   // 128x256 tiles (one CTA per SM) need the persistent / double-buffered-TMEM variant to pay off
   CUtensorMap ta, tb;
   int rc;

@@ -375,6 +375,29 @@ class Engine:
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
+    # ---- side stream: weight-gradient GEMMs and cross-sample reductions run beside the dgrad chain ----
+    overlap = True
+
+    def _fork(self, fn):
+        """Run fn() on the side stream after everything already queued on the current stream."""
+        if not self.overlap or self.timers is not None:
+            return fn()
+        main = torch.cuda.current_stream(self.device)
+        if getattr(self, "_side_stream", None) is None:
+            self._side_stream = torch.cuda.Stream(device=self.device)
+        ev = torch.cuda.Event()
+        ev.record(main)
+        self._side_stream.wait_event(ev)
+        with torch.cuda.stream(self._side_stream):
+            fn()
+        self._forked = True
+
+    def _join(self):
+        """Make the current stream wait for the side stream."""
+        if getattr(self, "_forked", False):
+            torch.cuda.current_stream(self.device).wait_stream(self._side_stream)
+            self._forked = False
+
     # CUDA-event timers on the launching stream (bench.py): timers = {"elbo": [], "gemm": [] ...}
     timers = None
 
@@ -411,6 +434,9 @@ class Engine:
         self._toc("gemm", t0)
 
     def _wgrad(self, name, A, lda, dY, lddy, rows, n_out=None, col0=0, accumulate=None):
+        self._fork(lambda: self._wgrad_now(name, A, lda, dY, lddy, rows, n_out, col0, accumulate))
+
+    def _wgrad_now(self, name, A, lda, dY, lddy, rows, n_out=None, col0=0, accumulate=None):
         ly = self.layers[name]
         dW = self.W(name, grad=True)
         n_out = ly.out_pad if n_out is None else n_out
@@ -472,10 +498,13 @@ class Engine:
             hp = self.layers["ench"].n_block
             self._fwd("ench", a, a.stride(0), self.act["ench"], self.dt, _abi.ACT_RELU, rows)
             h = self.act["ench"]
+            if "c" in heads:
+                if "z" in heads:
+                    self._fork(lambda: self._fwd("ch", h[:, hp:], h.stride(0), self.ch, F32, _abi.ACT_NONE, rows))
+                else:
+                    self._fwd("ch", h[:, hp:], h.stride(0), self.ch, F32, _abi.ACT_NONE, rows)
             if "z" in heads:
                 self._fwd("zh", h, h.stride(0), self.zh, F32, _abi.ACT_NONE, rows)
-            if "c" in heads:
-                self._fwd("ch", h[:, hp:], h.stride(0), self.ch, F32, _abi.ACT_NONE, rows)
         else:
             self._fwd("zh", a, a.stride(0), self.zh, F32, _abi.ACT_NONE, rows)
 
@@ -488,6 +517,8 @@ class Engine:
         ra.log_var = self.zh.data_ptr() + 4 * self.L
         ra.ld_zh = self.zh.stride(0)
         want_zeta = self.model == "dmvae" and self.cluster_sample
+        if want_zeta:
+            self._join()
         ra.logits = self.ch.data_ptr() if want_zeta else None
         ra.ld_logits = self.ch.stride(0) if want_zeta else 0
         ra.eps_in = self.eps_in.data_ptr() if eps_injected else None
@@ -537,14 +568,14 @@ class Engine:
         """Fused ELBO forward + backward and its cross-sample reductions."""
         s = (1.0 / rows) if inv_global_batch is None else inv_global_batch
         ea = self._elbo_args(X, xdt, rows, kl_ratio, s, recon_scale, klr_dev)
-        st = self._stream()
+        self._join()
         t0 = self._tic("elbo")
-        _abi.check(self.lib.dmvae_elbo_fwd_bwd(self.ctx, C.byref(ea), st))
+        _abi.check(self.lib.dmvae_elbo_fwd_bwd(self.ctx, C.byref(ea), self._stream()))
         self._toc("elbo", t0)
         gm = self.table("means", grad=True).data_ptr() if prior_grads else None
         gl = self.table("log_vars", grad=True).data_ptr() if prior_grads else None
-        _abi.check(self.lib.dmvae_elbo_reduce(self.ctx, C.byref(ea), gm, gl, 0, self.loss_out.data_ptr(),
-                                              self.red_ws.data_ptr(), st))
+        self._fork(lambda: _abi.check(self.lib.dmvae_elbo_reduce(self.ctx, C.byref(ea), gm, gl, 0, self.loss_out.data_ptr(),
+                                                                 self.red_ws.data_ptr(), self._stream())))
 
     # ------------------------------------------------------------------------------------------
     # backward
@@ -633,6 +664,7 @@ class Engine:
                     lp = self.layers[ec[i - 1]]
                     self._dgrad(nm, dy, dy.stride(0), a_in, a_in.stride(0), self.dact[ec[i - 1]], dt, rows, lp.n_valid,
                                 lp.n_block)
+        self._join()
 
     # ------------------------------------------------------------------------------------------
     # optimiser
@@ -688,6 +720,7 @@ class Engine:
         if backward:
             self.backward(rows, train_decoder=flags[0], train_z=flags[1], train_c=flags[2], train_trunk=flags[3])
             self._grads_dirty = True
+        self._join()
 
     use_graphs = True
 
