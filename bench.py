@@ -97,6 +97,11 @@ def synth_batches(n_rows, seed=1):
     return (rng.uniform(size=(n_rows, D)) < 0.1307).astype(np.uint8)
 
 
+def dbg(msg):
+    if os.environ.get("DMVAE_BENCH_DEBUG"):
+        print("[bench %s] %s" % (os.environ.get("RANK", "0"), msg), file=sys.stderr, flush=True)
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -138,9 +143,11 @@ def run_ours(args):
             dist.barrier(device_ids=[local_rank])
         torch.cuda.synchronize(dev)
 
+    dbg("setup done (dp mode %s)" % (dp.mode if dp else None))
     for i in range(W_):
         step(i)
     barrier()
+    dbg("warmup done")
     # ---- timed region 1: inputs resident in HBM ----
     clocks = ClockSampler(local_rank)
     if rank == 0:
@@ -154,6 +161,7 @@ def run_ours(args):
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
+    dbg("region 1 done: %.3f ms/step" % (ms / K_))
     launches = eng.launches() - l0
     # ---- timed region 2: end to end from pinned host memory through the public epoch loop ----
     NBH = min(K_, 128)                                              # host-resident batches of the e2e pass (<= 411 MB pinned)
@@ -171,6 +179,7 @@ def run_ours(args):
     e3.record()
     barrier()
     ms_e2e = e2.elapsed_time(e3)
+    dbg("region 2 done: %.3f ms/step" % (ms_e2e / K_))
     clk = clocks.stop() if rank == 0 else None
     # ---- timed region 3: per-kernel CUDA events (eager launches; a leading device-side sleep lets the host queue the
     #      whole step ahead of the GPU so that each event pair brackets one kernel, not a launch gap) ----
@@ -186,14 +195,14 @@ def run_ours(args):
     adam_ms = eng.timer_ms("adam")
     eng.timers = None
     eng.use_graphs = True
+    dbg("region 3 done")
 
     t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, ms_e2e = float(t[0]), float(t[1])
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        _finish(world, dev)
         return
     pk = peaks()
     value = world * B * K_ / (ms * 1e-3)
@@ -231,9 +240,19 @@ def run_ours(args):
     }
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(bounded_seconds=20.0)
-    print(json.dumps(out))
+    print(json.dumps(out), flush=True)
+    _finish(world, dev)
+
+
+def _finish(world, dev):
+    """Multi-rank teardown: captured graphs hold NCCL / symmetric-memory work, and destroying the process group under
+    them can block; every rank synchronises and leaves without running the destructors."""
     if world > 1:
-        dist.destroy_process_group()
+        import torch
+        torch.cuda.synchronize(dev)
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def cpu_baseline(bounded_seconds=20.0, batch=256):

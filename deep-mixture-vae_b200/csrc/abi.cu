@@ -235,7 +235,7 @@ extern "C" int dmvae_step_tick(dmvae_ctx* ctx, void* state_dev, float lr, float 
 // The caller brackets the launch with a cross-rank barrier on each side.
 // ---------------------------------------------------------------------------------------------
 struct DpPeers {
-  const float* grads[8];
+  float* grads[8];
   float* params[8];
   __nv_bfloat16* pbf[8];
 };
@@ -254,6 +254,9 @@ __global__ void __launch_bounds__(256) dp_reduce_adam_kernel(DpPeers peers, int 
       float4 t = reinterpret_cast<const float4*>(peers.grads[r])[i];
       g.x += t.x; g.y += t.y; g.z += t.z; g.w += t.w;
     }
+    // this rank is the only reader of element i of every replica's gradient: clear it for the next step's
+    // split-K accumulation
+    for (int r = 0; r < world; ++r) reinterpret_cast<float4*>(peers.grads[r])[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     float4 p = reinterpret_cast<float4*>(peers.params[rank])[i];
     const int64_t li = i - begin4;
     float4 mm = reinterpret_cast<float4*>(m)[li];
@@ -270,7 +273,7 @@ __global__ void __launch_bounds__(256) dp_reduce_adam_kernel(DpPeers peers, int 
   }
 }
 
-extern "C" int dmvae_dp_reduce_adam(dmvae_ctx* ctx, int rank, int world, const float* const* grads_peers_host,
+extern "C" int dmvae_dp_reduce_adam(dmvae_ctx* ctx, int rank, int world, float* const* grads_peers_host,
                                     float* const* params_peers_host, void* const* params_bf16_peers_host, float* m,
                                     float* v, int64_t n, int64_t shard_begin, int64_t shard_end, float lr_t,
                                     const float* lr_t_dev, float beta1, float beta2, float eps, void* stream) {

@@ -1,0 +1,172 @@
+"""Data parallelism for the training step (new functionality: the reference is single-device).
+
+One process per GPU (torchrun); ``torch.distributed`` is the plumbing.  The minibatch is sharded by rank, every
+rank scales its gradients by 1/global_batch inside the fused ELBO kernel, and the Philox counters are offset by
+the global row index, so an N-GPU step computes exactly the single-GPU step of the concatenated batch.
+
+The only exchange is the sum of the flat fp32 gradient buffer, fused with the Adam update:
+
+  mode "p2p"  : the flat parameter / gradient buffers live in symmetric (peer-mapped) memory; ONE kernel per rank
+                (dmvae_dp_reduce_adam) reads its 1/N shard of every peer's gradients over NVLink, sums them in a
+                fixed order, applies Adam to the shard and stores the new fp32 + bf16 parameters into every
+                replica (reduce-scatter + Adam + all-gather without a round trip through HBM).
+  mode "nccl" : ncclAllReduce of the flat gradient buffer, then the replicated flat Adam kernel (baseline).
+
+The host-side arithmetic (shard ranges, bucket layout) is device-agnostic and covered by gloo tests on CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n: int, rank: int, world: int, align: int = 4) -> Tuple[int, int]:
+    """[begin, end) of rank's shard of n elements; boundaries are multiples of ``align`` (float4 access)."""
+    per = (n + world - 1) // world
+    per = (per + align - 1) // align * align
+    b = min(n, rank * per)
+    e = min(n, b + per)
+    return b, e
+
+
+def global_row_offset(rank: int, rows_per_rank: int) -> int:
+    """Global index of a rank's first sample: the Philox counter offset that makes an N-GPU run reproduce the
+    noise of the 1-GPU run on the concatenated batch."""
+    return rank * rows_per_rank
+
+
+def allreduce_adam_reference(grads: torch.Tensor, apply_adam, group=None):
+    """Device-agnostic statement of mode "nccl": sum the gradients over ranks, then the same Adam everywhere."""
+    dist.all_reduce(grads, op=dist.ReduceOp.SUM, group=group)
+    apply_adam(0, grads.numel(), grads)
+
+
+def sharded_adam_reference(grads: torch.Tensor, params: torch.Tensor, apply_adam, rank: int, world: int, group=None):
+    """Device-agnostic statement of mode "p2p" with collectives: reduce-scatter the gradient shards, Adam on the owned
+    shard, all-gather the parameters.  Must give the same parameters as allreduce_adam_reference."""
+    n = grads.numel()
+    per = shard_range(n, 0, world)[1]
+    padded = torch.zeros(per * world, dtype=grads.dtype, device=grads.device)
+    padded[:n] = grads
+    mine = torch.zeros(per, dtype=grads.dtype, device=grads.device)
+    parts = list(padded.view(world, per).unbind(0))
+    dist.reduce_scatter(mine, [p.contiguous() for p in parts], op=dist.ReduceOp.SUM, group=group) \
+        if dist.get_backend(group) != "gloo" else _gloo_reduce_scatter(mine, parts, rank, group)
+    b, e = shard_range(n, rank, world)
+    apply_adam(b, e, mine[: e - b])
+    pp = torch.zeros(per * world, dtype=params.dtype, device=params.device)
+    pp[:n] = params
+    outs = [torch.zeros(per, dtype=params.dtype, device=params.device) for _ in range(world)]
+    dist.all_gather(outs, pp.view(world, per)[rank].contiguous(), group=group)
+    params.copy_(torch.cat(outs)[:n])
+
+
+def _gloo_reduce_scatter(out, parts, rank, group):
+    # gloo has no reduce_scatter: all-reduce every part and keep ours
+    for r, p in enumerate(parts):
+        t = p.clone()
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        if r == rank:
+            out.copy_(t)
+
+
+class DataParallel:
+    """Binds an Engine to the default process group."""
+
+    def __init__(self, engine, mode: str = "auto", group=None):
+        from . import _abi
+        self._abi = _abi
+        self.eng = engine
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        engine.world, engine.rank = self.world, self.rank
+        engine.dp = self
+        self.mode = mode
+        self.hdl = None
+        if mode in ("auto", "p2p"):
+            try:
+                self._setup_symmetric()
+                self.mode = "p2p"
+            except Exception as ex:                      # no peer access / symmetric memory unavailable
+                if mode == "p2p":
+                    raise
+                self.mode = "nccl"
+                self.fallback_reason = repr(ex)
+        # identical parameters everywhere (rank 0's initialisation)
+        dist.broadcast(engine.params, src=0, group=group)
+        engine.sync_operand_copy()
+        torch.cuda.synchronize(engine.device)
+        self.shard = shard_range(engine.n_params, self.rank, self.world)
+        self._opt_shards = {}
+
+    # ---- symmetric memory -------------------------------------------------------------------------------
+    def _setup_symmetric(self):
+        import torch.distributed._symmetric_memory as symm_mem
+        eng = self.eng
+        P = eng.n_params
+        nbytes = 4 * P + 4 * P + (2 * P if eng.params_op is not None else 0)
+        buf = symm_mem.empty(nbytes, dtype=torch.uint8, device=eng.device)
+        grp = self.group if self.group is not None else dist.group.WORLD
+        hdl = symm_mem.rendezvous(buf, grp)
+        params = buf[: 4 * P].view(torch.float32)
+        grads = buf[4 * P: 8 * P].view(torch.float32)
+        params.copy_(eng.params)
+        grads.zero_()
+        eng.params, eng.grads = params, grads
+        if eng.params_op is not None:
+            pop = buf[8 * P: 10 * P].view(torch.bfloat16)
+            pop.copy_(eng.params_op)
+            eng.params_op = pop
+        eng._graphs = {}                                  # captured graphs hold the old pointers
+        if hasattr(eng, "_graph_replay_launches"):
+            pass
+        self.hdl, self._symm_buf = hdl, buf
+        ptrs = [int(p) for p in hdl.buffer_ptrs]
+        VP = C.c_void_p * self.world
+        self._g_ptrs = VP(*[p + 4 * P for p in ptrs])
+        self._p_ptrs = VP(*[p for p in ptrs])
+        self._b_ptrs = VP(*[(p + 8 * P) if eng.params_op is not None else 0 for p in ptrs])
+
+    def _opt_shard_state(self, opt):
+        """Adam slots of the owned shard only (the other ranks own the rest)."""
+        key = id(opt)
+        if key not in self._opt_shards:
+            b, e = self.shard
+            n = max(e - b, 4)
+            self._opt_shards[key] = (torch.zeros(n, dtype=torch.float32, device=self.eng.device),
+                                     torch.zeros(n, dtype=torch.float32, device=self.eng.device))
+        return self._opt_shards[key]
+
+    # ---- the exchange + update ---------------------------------------------------------------------------
+    def update(self, opt, use_dev: bool = False):
+        eng, abi = self.eng, self._abi
+        lr_t = 0.0 if use_dev else opt.next_lr_t()
+        lr_dev = (opt.state_dev.data_ptr() + 12) if use_dev else None
+        if self.mode == "p2p":
+            m, v = self._opt_shard_state(opt)
+            b, e = self.shard
+            self.hdl.barrier(channel=0)                   # every rank's gradients are complete
+            abi.check(eng.lib.dmvae_dp_reduce_adam(eng.ctx, self.rank, self.world, self._g_ptrs, self._p_ptrs,
+                                                   self._b_ptrs, m.data_ptr(), v.data_ptr(), eng.n_params, b, e, lr_t,
+                                                   lr_dev, opt.beta1, opt.beta2, opt.eps, eng._stream()))
+            self.hdl.barrier(channel=1)                   # every replica updated, every gradient shard cleared
+        else:
+            dist.all_reduce(eng.grads, op=dist.ReduceOp.SUM, group=self.group)
+            abi.check(eng.lib.dmvae_adam(eng.ctx, eng.params.data_ptr(), eng.grads.data_ptr(), opt.m.data_ptr(),
+                                         opt.v.data_ptr(), eng.params_op.data_ptr() if eng.params_op is not None else None,
+                                         eng.n_params, lr_t, lr_dev, opt.beta1, opt.beta2, opt.eps, 1.0, 1, eng._stream()))
+        eng._grads_dirty = False
+
+    def train_step(self, X, rows, opt, kl_ratio=1.0):
+        self.eng.train_step(X, rows, opt, kl_ratio=kl_ratio)
+
+    def run_epoch(self, host, batch_size, opt, kl_ratio=1.0, max_steps=None):
+        """Every rank iterates over ITS host shard; the returned loss is the global mean (one all-reduce per epoch)."""
+        loss = self.eng.run_epoch(host, batch_size, opt, kl_ratio, "all", max_steps)
+        t = torch.tensor([loss], dtype=torch.float64, device=self.eng.device)
+        dist.all_reduce(t, group=self.group)
+        return float(t[0])

@@ -118,6 +118,11 @@ class Engine:
         self.step_count = 0
         self.split_k_wgrad = split_k_wgrad
         self.world, self.rank = 1, 0
+        self.dp = None
+        self._graphs = {}
+        self._graph_replay_launches = 0
+        self.klr_dev = torch.ones(1, dtype=torch.float32, device=self.device)
+        self._klr_host = 1.0
         ctx = C.c_void_p()
         _abi.check(self.lib.dmvae_ctx_create(self.device.index or 0, C.byref(ctx)))
         self.ctx = ctx
@@ -730,26 +735,35 @@ class Engine:
         Without injected noise the step is captured once per (input buffer, rows, mode, optimiser) into a CUDA graph
         and replayed: per-step scalars (Adam's lr_t, the Philox step, kl_ratio) live in device memory."""
         use_graph = self.use_graphs if graph is None else graph
-        if use_graph and eps is None and gumbel is None and self.world == 1:
+        if use_graph and eps is None and gumbel is None:
             return self._train_step_graph(X, rows, opt, kl_ratio, mode, recon_scale)
-        self.forward_backward(X, rows, eps, gumbel, kl_ratio, None, 0, recon_scale, True, mode)
-        self.adam(opt, zero_grads=True)
+        inv, off = self._dp_scale(rows)
+        self.forward_backward(X, rows, eps, gumbel, kl_ratio, inv, off, recon_scale, True, mode)
+        self._update(opt)
         self.step_count += 1
 
+    def _dp_scale(self, rows):
+        """(1 / global batch, global index of this rank's first row): data-parallel shards."""
+        if self.world == 1:
+            return None, 0
+        return 1.0 / (rows * self.world), self.rank * rows
+
+    def _update(self, opt, use_dev: bool = False):
+        if self.dp is None:
+            self.adam(opt, zero_grads=True, use_dev=use_dev)
+        else:
+            self.dp.update(opt, use_dev)
+
     def _train_step_graph(self, X, rows, opt, kl_ratio, mode, recon_scale):
-        if not hasattr(self, "_graphs"):
-            self._graphs = {}
-            self._graph_replay_launches = 0
-            self.klr_dev = torch.ones(1, dtype=torch.float32, device=self.device)
-            self._klr_host = 1.0
         key = (X.data_ptr(), X.dtype, X.stride(0), rows, mode, id(opt), float(recon_scale),
                float(kl_ratio) if mode != "all" else None)
         ent = self._graphs.get(key)
         if ent is None:
             # first use of this signature: one eager step (also warms the TMA-descriptor cache and the kernels'
             # shared-memory attributes), then capture the same sequence for every later step
-            self.forward_backward(X, rows, None, None, kl_ratio, None, 0, recon_scale, True, mode)
-            self.adam(opt, zero_grads=True)
+            inv, off = self._dp_scale(rows)
+            self.forward_backward(X, rows, None, None, kl_ratio, inv, off, recon_scale, True, mode)
+            self._update(opt)
             self.step_count += 1
             torch.cuda.current_stream(self.device).synchronize()
             g = torch.cuda.CUDAGraph()
@@ -757,8 +771,8 @@ class Engine:
             with torch.cuda.graph(g):
                 _abi.check(self.lib.dmvae_step_tick(self.ctx, opt.state_dev.data_ptr(), opt.lr, opt.beta1, opt.beta2,
                                                     self._stream()))
-                self.forward_backward(X, rows, None, None, kl_ratio, None, 0, recon_scale, True, mode, dev_state=opt)
-                self.adam(opt, zero_grads=True, use_dev=True)
+                self.forward_backward(X, rows, None, None, kl_ratio, inv, off, recon_scale, True, mode, dev_state=opt)
+                self._update(opt, use_dev=True)
             n_nodes = int(self.lib.dmvae_ctx_launch_count(self.ctx)) - l0
             self._graphs[key] = (g, n_nodes)
             self._grads_dirty = False

