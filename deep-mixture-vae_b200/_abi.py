@@ -99,6 +99,9 @@ SIGNATURES = {
     "dmvae_moe_fwd_bwd": (c_int, [c_void_p, C.POINTER(MoeArgs), c_void_p]),
     "dmvae_softmax_bwd_add": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int64, c_void_p, c_int, c_int64,
                                       c_int, c_int, c_void_p]),
+    "dmvae_softmax_rows": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p]),
+    "dmvae_reduce_columns": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_float, c_void_p, c_void_p]),
+    "dmvae_stage_features": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_int, c_int64, c_int, c_void_p]),
     "dmvae_adam": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_void_p, c_float,
                            c_float, c_float, c_float, c_int, c_void_p]),
     "dmvae_step_tick": (c_int, [c_void_p, c_void_p, c_float, c_float, c_float, c_void_p]),

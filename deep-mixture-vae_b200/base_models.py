@@ -285,7 +285,7 @@ class DeepMixtureVAE(VAE):
         return dict(model="dmvae", input_type=self.input_type, input_dim=self.input_dim, latent_dim=self.latent_dim,
                     n_classes=self.n_classes, trunk=self.hidden[:2], head=self.hidden[2], decoder=self.decoder_sizes,
                     name=self.name, gemm_dtype=self.gemm_dtype, seed=self.seed, max_rows=self.max_batch,
-                    cluster_sample=self.cluster_sample, temperature=self.temperature)
+                    cluster_sample=self.cluster_sample, temperature=self.temperature, moe=getattr(self, "moe_config", None))
 
     def define_pretrain_step(self, vae_lr, prior_lr):
         """base_models.py:304-321: two more Adam instances - recon_loss over everything, latent_loss over the
@@ -419,7 +419,7 @@ class VaDE(VAE):
     def _engine_kwargs(self):
         return dict(model="vade", input_type=self.input_type, input_dim=self.input_dim, latent_dim=self.latent_dim,
                     n_classes=self.n_classes, trunk=self.hidden, head=0, decoder=self.decoder_sizes, name=self.name,
-                    gemm_dtype=self.gemm_dtype, seed=self.seed, max_rows=self.max_batch)
+                    gemm_dtype=self.gemm_dtype, seed=self.seed, max_rows=self.max_batch, moe=getattr(self, "moe_config", None))
 
     def define_pretrain_step(self, vae_lr, _prior_lr=None):
         """base_models.py:574-580."""

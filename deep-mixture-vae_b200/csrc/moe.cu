@@ -134,7 +134,78 @@ __global__ void softmax_bwd_add_kernel(int rows, int K, const float* __restrict_
     for (int k = K; k < cols; ++k) d[k] = from_f32<TD>(0.f);
 }
 
+__global__ void softmax_rows_kernel(const float* __restrict__ sc, int64_t ld, int rows, int K, float* __restrict__ q) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= rows) return;
+  const float* s = sc + (int64_t)row * ld;
+  float mx = s[0];
+  for (int k = 1; k < K; ++k) mx = fmaxf(mx, s[k]);
+  float den = 0.f;
+  for (int k = 0; k < K; ++k) den += expf(s[k] - mx);
+  for (int k = 0; k < K; ++k) q[(int64_t)row * K + k] = expf(s[k] - mx) / den;
+}
+
+// out[c] = scale * sum_r src[r, c]; one block, fixed order (deterministic)
+__global__ void __launch_bounds__(256) reduce_columns_kernel(const float* __restrict__ src, int64_t ld, int rows, int cols,
+                                                             float scale, float* __restrict__ out) {
+  __shared__ float sm[256];
+  for (int c = 0; c < cols; ++c) {
+    float acc = 0.f;
+    for (int r = threadIdx.x; r < rows; r += 256) acc += src[(int64_t)r * ld + c];
+    sm[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+      if (threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) out[c] = scale * sm[0];
+    __syncthreads();
+  }
+}
+
+template <typename TO>
+__global__ void stage_features_kernel(const float* __restrict__ src, int64_t ld, int rows, int n, int relu,
+                                      TO* __restrict__ out, int64_t ld_out, int out_cols) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int r = warp; r < rows; r += nwarps)
+    for (int j = lane; j < out_cols; j += 32) {
+      float v = j < n ? src[(int64_t)r * ld + j] : (j == n ? 1.f : 0.f);
+      if (relu && j < n) v = fmaxf(v, 0.f);
+      out[(int64_t)r * ld_out + j] = from_f32<TO>(v);
+    }
+}
+
 }  // namespace
+
+extern "C" int dmvae_softmax_rows(dmvae_ctx* ctx, const float* scores, int64_t ld, int rows, int K, float* q, void* stream) {
+  DMVAE_CHECK_ARG(ctx && scores && q && rows >= 0 && K > 0 && ld >= K, "softmax_rows: bad arguments");
+  if (rows == 0) return DMVAE_OK;
+  softmax_rows_kernel<<<(rows + 127) / 128, 128, 0, (cudaStream_t)stream>>>(scores, ld, rows, K, q);
+  DMVAE_LAUNCH_CHECK(ctx);
+  return DMVAE_OK;
+}
+
+extern "C" int dmvae_reduce_columns(dmvae_ctx* ctx, const float* src, int64_t ld, int rows, int cols, float scale, float* out,
+                                    void* stream) {
+  DMVAE_CHECK_ARG(ctx && src && out && rows >= 0 && cols > 0 && ld >= cols, "reduce_columns: bad arguments");
+  reduce_columns_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(src, ld, rows, cols, scale, out);
+  DMVAE_LAUNCH_CHECK(ctx);
+  return DMVAE_OK;
+}
+
+extern "C" int dmvae_stage_features(dmvae_ctx* ctx, const float* src, int64_t ld, int rows, int n, int relu, void* out,
+                                    int out_dtype, int64_t ld_out, int out_cols, void* stream) {
+  DMVAE_CHECK_ARG(ctx && src && out && rows >= 0 && n > 0 && ld >= n && out_cols > n && out_cols <= ld_out, "stage_features: bad arguments");
+  if (rows == 0) return DMVAE_OK;
+  int blocks = min(ctx->sm_count * 8, (rows + 7) / 8);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (out_dtype == DMVAE_F32) stage_features_kernel<float><<<blocks, 256, 0, st>>>(src, ld, rows, n, relu, (float*)out, ld_out, out_cols);
+  else if (out_dtype == DMVAE_BF16) stage_features_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(src, ld, rows, n, relu, (__nv_bfloat16*)out, ld_out, out_cols);
+  else { dmvae_set_error("stage_features: out_dtype %d unsupported", out_dtype); return DMVAE_ERR_INVALID; }
+  DMVAE_LAUNCH_CHECK(ctx);
+  return DMVAE_OK;
+}
 
 extern "C" int dmvae_moe_fwd_bwd(dmvae_ctx* ctx, const dmvae_moe_args* a, void* stream) {
   DMVAE_CHECK_ARG(ctx && a, "moe: NULL argument");

@@ -58,85 +58,30 @@ class Layer:
         return self.in_pad * self.out_pad
 
 
-_TORCH_DT = {F32: torch.float32, BF16: torch.bfloat16, U8: torch.uint8}
+class Layout:
+    """Pure-Python description of the padded parameter layout of one model (no CUDA needed): the dense layers, where
+    each reference variable lives inside them, and the offsets in the flat fp32 buffer."""
 
-
-class AdamState:
-    """Slots of one tf.train.AdamOptimizer instance (base_models.py:102-110, :307-321)."""
-
-    def __init__(self, n: int, device, lr: float, beta1=0.9, beta2=0.999, eps=1e-8):
-        self.m = torch.zeros(n, dtype=torch.float32, device=device)
-        self.v = torch.zeros(n, dtype=torch.float32, device=device)
-        self.t = 0
-        self.lr, self.beta1, self.beta2, self.eps = lr, beta1, beta2, eps
-        # device-resident {uint64 step; uint32 t; float lr_t} read by the kernels under CUDA-graph replay
-        self.state_dev = torch.zeros(4, dtype=torch.int32, device=device)
-        self.state_valid = False
-
-    def next_lr_t(self) -> float:
-        self.t += 1
-        self.state_valid = False
-        return self.lr * math.sqrt(1.0 - self.beta2 ** self.t) / (1.0 - self.beta1 ** self.t)
-
-    def upload_state(self, step_count: int):
-        """device step = step_count - 1 and t = self.t: the graph's first node (dmvae_step_tick) increments both."""
-        st = np.zeros(1, dtype=[("step", "<u8"), ("t", "<u4"), ("lr_t", "<f4")])
-        st["step"] = (step_count - 1) & 0xFFFFFFFFFFFFFFFF
-        st["t"] = self.t
-        self.state_dev.copy_(torch.from_numpy(st.view(np.int32).copy()), non_blocking=False)
-        self.state_valid = True
-
-
-class Engine:
-    """Kernels + buffers for one DMVAE / VaDE model (optionally with an MoE expert head)."""
-
-    def __init__(self, *, model: str, input_type: str, input_dim: int, latent_dim: int, n_classes: int,
-                 trunk: Tuple[int, ...], head: int, decoder: Tuple[int, ...], name: str,
-                 gemm_dtype: str = "bf16", device=None, seed: int = 0, max_rows: int = 4096,
-                 cluster_sample: bool = False, temperature: float = 1.0, decoded_dtype: Optional[str] = None,
-                 moe: Optional[dict] = None, split_k_wgrad: Optional[int] = None):
-        if not torch.cuda.is_available():
-            raise RuntimeError("dmvae_b200 needs a CUDA device: there is no CPU fallback")
-        if input_type not in ("binary", "real"):
-            raise NotImplementedError(input_type)                      # base_models.py:84-85
+    def __init__(self, *, model, input_dim, latent_dim, n_classes, trunk, head, decoder, name, moe=None):
         if model not in ("dmvae", "vade"):
             raise NotImplementedError(model)
-        self.lib = _abi.load()
-        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
-        self.model, self.input_type, self.name = model, input_type, name
+        self.model, self.name = model, name
         self.D, self.L, self.K = input_dim, latent_dim, n_classes
-        self.trunk, self.head, self.decoder = tuple(trunk), head, tuple(decoder)
-        self.cluster_sample, self.temperature = cluster_sample, float(temperature)
-        self.dt = {"bf16": BF16, "fp32": F32, "f32": F32}[gemm_dtype]
-        self.tdt = _TORCH_DT[self.dt]
-        self.dec_dt = self.dt if decoded_dtype is None else {"bf16": BF16, "fp32": F32, "f32": F32}[decoded_dtype]
-        if self.dt == F32:
-            self.dec_dt = F32
-        self.moe = moe
-        self.seed = seed
-        self.noise_seed = seed + 2
-        self.step_count = 0
-        self.split_k_wgrad = split_k_wgrad
-        self.world, self.rank = 1, 0
-        self.dp = None
-        self._graphs = {}
-        self._graph_replay_launches = 0
-        self.klr_dev = torch.ones(1, dtype=torch.float32, device=self.device)
-        self._klr_host = 1.0
-        ctx = C.c_void_p()
-        _abi.check(self.lib.dmvae_ctx_create(self.device.index or 0, C.byref(ctx)))
-        self.ctx = ctx
-        if self.dt == BF16 and not self.lib.dmvae_ctx_has_tcgen05(self.ctx):
-            raise RuntimeError("gemm_dtype='bf16' needs an sm_100 (B200) device with TMA; no fallback exists")
+        self.trunk, self.head, self.decoder, self.moe = tuple(trunk), head, tuple(decoder), moe
         self._build_layers()
-        self._alloc_params()
-        self.max_rows = 0
-        self._alloc_activations(max_rows)
-        self.init_variables(seed)
+        off = 0
+        for ly in self.layers.values():
+            ly.offset = off
+            off += ly.size
+        self.tab_size = ((self.K * self.L + 63) // 64) * 64
+        self.off_means = off
+        self.off_log_vars = off + self.tab_size
+        self.n_params = off + 2 * self.tab_size
 
-    # ------------------------------------------------------------------------------------------
-    # layer table
-    # ------------------------------------------------------------------------------------------
+    def reference_parameter_count(self) -> int:
+        """Number of reference parameters that receive a gradient (SURVEY 8: 4 373 014 for cfg1/2)."""
+        return int(sum(int(np.prod(v.shape)) for v in self.vars.values()))
+
     def _build_layers(self):
         D, L, K, n = self.D, self.L, self.K, self.name
         self.layers: Dict[str, Layer] = {}
@@ -207,15 +152,91 @@ class Engine:
         self.vars[n + "/representation/means"] = VarView("prior_means", "table", 0, L, (K, L), "normal")
         self.vars[n + "/representation/log_vars"] = VarView("prior_log_vars", "table", 0, L, (K, L), "zeros")
 
+
+_TORCH_DT = {F32: torch.float32, BF16: torch.bfloat16, U8: torch.uint8}
+
+
+class AdamState:
+    """Slots of one tf.train.AdamOptimizer instance (base_models.py:102-110, :307-321)."""
+
+    def __init__(self, n: int, device, lr: float, beta1=0.9, beta2=0.999, eps=1e-8):
+        self.m = torch.zeros(n, dtype=torch.float32, device=device)
+        self.v = torch.zeros(n, dtype=torch.float32, device=device)
+        self.t = 0
+        self.lr, self.beta1, self.beta2, self.eps = lr, beta1, beta2, eps
+        # device-resident {uint64 step; uint32 t; float lr_t} read by the kernels under CUDA-graph replay
+        self.state_dev = torch.zeros(4, dtype=torch.int32, device=device)
+        self.state_valid = False
+
+    def next_lr_t(self) -> float:
+        self.t += 1
+        self.state_valid = False
+        return self.lr * math.sqrt(1.0 - self.beta2 ** self.t) / (1.0 - self.beta1 ** self.t)
+
+    def upload_state(self, step_count: int):
+        """device step = step_count - 1 and t = self.t: the graph's first node (dmvae_step_tick) increments both."""
+        st = np.zeros(1, dtype=[("step", "<u8"), ("t", "<u4"), ("lr_t", "<f4")])
+        st["step"] = (step_count - 1) & 0xFFFFFFFFFFFFFFFF
+        st["t"] = self.t
+        self.state_dev.copy_(torch.from_numpy(st.view(np.int32).copy()), non_blocking=False)
+        self.state_valid = True
+
+
+class Engine:
+    """Kernels + buffers for one DMVAE / VaDE model (optionally with an MoE expert head)."""
+
+    def __init__(self, *, model: str, input_type: str, input_dim: int, latent_dim: int, n_classes: int,
+                 trunk: Tuple[int, ...], head: int, decoder: Tuple[int, ...], name: str,
+                 gemm_dtype: str = "bf16", device=None, seed: int = 0, max_rows: int = 4096,
+                 cluster_sample: bool = False, temperature: float = 1.0, decoded_dtype: Optional[str] = None,
+                 moe: Optional[dict] = None, split_k_wgrad: Optional[int] = None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("dmvae_b200 needs a CUDA device: there is no CPU fallback")
+        if input_type not in ("binary", "real"):
+            raise NotImplementedError(input_type)                      # base_models.py:84-85
+        if model not in ("dmvae", "vade"):
+            raise NotImplementedError(model)
+        self.lib = _abi.load()
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.model, self.input_type, self.name = model, input_type, name
+        self.D, self.L, self.K = input_dim, latent_dim, n_classes
+        self.trunk, self.head, self.decoder = tuple(trunk), head, tuple(decoder)
+        self.cluster_sample, self.temperature = cluster_sample, float(temperature)
+        self.dt = {"bf16": BF16, "fp32": F32, "f32": F32}[gemm_dtype]
+        self.tdt = _TORCH_DT[self.dt]
+        self.dec_dt = self.dt if decoded_dtype is None else {"bf16": BF16, "fp32": F32, "f32": F32}[decoded_dtype]
+        if self.dt == F32:
+            self.dec_dt = F32
+        self.moe = moe
+        self.seed = seed
+        self.noise_seed = seed + 2
+        self.step_count = 0
+        self.split_k_wgrad = split_k_wgrad
+        self.world, self.rank = 1, 0
+        self.dp = None
+        self._graphs = {}
+        self._graph_replay_launches = 0
+        self.klr_dev = torch.ones(1, dtype=torch.float32, device=self.device)
+        self._klr_host = 1.0
+        ctx = C.c_void_p()
+        _abi.check(self.lib.dmvae_ctx_create(self.device.index or 0, C.byref(ctx)))
+        self.ctx = ctx
+        if self.dt == BF16 and not self.lib.dmvae_ctx_has_tcgen05(self.ctx):
+            raise RuntimeError("gemm_dtype='bf16' needs an sm_100 (B200) device with TMA; no fallback exists")
+        self.layout = Layout(model=model, input_dim=input_dim, latent_dim=latent_dim, n_classes=n_classes, trunk=trunk,
+                             head=head, decoder=decoder, name=name, moe=moe)
+        for k in ("layers", "vars", "enc_chain", "dec_chain", "dead_vars", "last_hidden", "tab_size", "off_means",
+                  "off_log_vars", "n_params"):
+            setattr(self, k, getattr(self.layout, k))
+        self._alloc_params()
+        self.max_rows = 0
+        self._alloc_activations(max_rows)
+        self.init_variables(seed)
+
+    # ------------------------------------------------------------------------------------------
+    # layer table
+    # ------------------------------------------------------------------------------------------
     def _alloc_params(self):
-        off = 0
-        for ly in self.layers.values():
-            ly.offset = off
-            off += ly.size
-        self.tab_size = ((self.K * self.L + 63) // 64) * 64
-        self.off_means = off
-        self.off_log_vars = off + self.tab_size
-        self.n_params = off + 2 * self.tab_size
         dev = self.device
         self.params = torch.zeros(self.n_params, dtype=torch.float32, device=dev)
         self.grads = torch.zeros(self.n_params, dtype=torch.float32, device=dev)
@@ -240,8 +261,7 @@ class Engine:
         return list(self.vars.keys()) + list(self.dead_vars.keys())
 
     def trainable_size(self) -> int:
-        """Number of reference parameters that receive a gradient (SURVEY 8: 4 373 014 for cfg1/2)."""
-        return int(sum(int(np.prod(v.shape)) for v in self.vars.values()))
+        return self.layout.reference_parameter_count()
 
     def _view(self, vv: VarView, grad=False) -> torch.Tensor:
         if vv.kind == "table":
@@ -376,6 +396,7 @@ class Engine:
             self.moe_cls = torch.zeros(B, dtype=torch.int32, device=dev)
             self.moe_dinp = z(self.layers["moe"].in_pad, f32)
             self.y_buf = z(O, f32)
+            self.moe_loss = torch.zeros(2, dtype=f32, device=dev)
 
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
@@ -586,13 +607,13 @@ class Engine:
     # backward
     # ------------------------------------------------------------------------------------------
     def backward(self, rows: int, dmean_extra: Optional[torch.Tensor] = None, train_decoder=True, train_z=True,
-                 train_c=True, train_trunk=True):
+                 train_c=True, train_trunk=True, through_decoder=True):
         """Gradient GEMMs from d_decoded / d_logits / KL-side gradients back to every parameter."""
         dt = self.dt
         # ---- decoder ----
         chain = self.dec_chain
         a_last = self.act[chain[-1]]
-        if train_decoder or train_z:
+        if through_decoder and (train_decoder or train_z):
             if train_decoder:
                 self._wgrad("decx", a_last, a_last.stride(0), self.ddecoded, self.ddecoded.stride(0), rows)
             ly_prev = self.layers[chain[-1]]
@@ -726,6 +747,85 @@ class Engine:
             self.backward(rows, train_decoder=flags[0], train_z=flags[1], train_c=flags[2], train_trunk=flags[3])
             self._grads_dirty = True
         self._join()
+
+    # ------------------------------------------------------------------------------------------
+    # mixture-of-experts head (models.py:53-111, :149-163)
+    # ------------------------------------------------------------------------------------------
+    def moe_step(self, X: torch.Tensor, Y: torch.Tensor, rows: int, opt: Optional[AdamState], eps=None, gumbel=None,
+                 kl_ratio: float = 1.0, train: bool = True):
+        """Gate = q(c|x) of the VAE, experts = one dense GEMM over all experts; supervised loss (+ the VAE loss when
+        lossVAE).  Fills moe_loss = [supervised loss, error] and loss_out (VAE terms when lossVAE)."""
+        cfg = self.moe
+        E, O, lossVAE, feat = cfg["n_experts"], cfg["output_dim"], bool(cfg["lossVAE"]), bool(cfg["featLearn"])
+        if rows > self.max_rows:
+            self._alloc_activations(rows)
+        if getattr(self, "_params_dirty", False):
+            self.sync_operand_copy()
+        if train and getattr(self, "_grads_dirty", False):
+            self.zero_grads()
+        if eps is not None:
+            self.eps_in[:rows].copy_(eps.reshape(rows, self.L))
+        if gumbel is not None:
+            self.gumbel_in[:rows].copy_(gumbel.reshape(rows, self.K))
+        self.y_buf[:rows].copy_(Y.reshape(rows, O))
+        st = self._stream
+        Xs, xdt = self.stage_input(X, rows)
+        full = lossVAE or self.model == "vade"
+        if full:
+            self.encode(rows)
+            self.reparam(rows, eps is not None, gumbel is not None)
+            self.decode(rows)
+            self.elbo(Xs, xdt, rows, kl_ratio if lossVAE else 0.0, None, 1.0 if lossVAE else 0.0, prior_grads=lossVAE)
+            self._join()
+        else:
+            self.encode(rows, heads=("z", "c") if feat else ("c",))
+            self._join()
+            _abi.check(self.lib.dmvae_softmax_rows(self.ctx, self.ch.data_ptr(), self.ch.stride(0), rows, self.K,
+                                                   self.qc.data_ptr(), st()))
+        # expert inputs
+        if feat:
+            _abi.check(self.lib.dmvae_stage_features(self.ctx, self.zh.data_ptr(), self.zh.stride(0), rows, self.L, 1,
+                                                     self.moe_in.data_ptr(), self.dt, self.moe_in.stride(0),
+                                                     self.moe_in.shape[1], st()))
+            a_in = self.moe_in
+        else:
+            a_in = self.act["x"]
+        self._fwd("moe", a_in, a_in.stride(0), self.moe_pred, F32, _abi.ACT_NONE, rows)
+        ma = _abi.MoeArgs()
+        ma.classification, ma.rows, ma.E, ma.O = int(bool(cfg["classification"])), rows, E, O
+        ma.pred, ma.ld_pred = self.moe_pred.data_ptr(), self.moe_pred.stride(0)
+        ma.gate, ma.ld_gate = self.qc.data_ptr(), self.K
+        ma.Y, ma.ldy = self.y_buf.data_ptr(), O
+        ma.inv_global_batch = 1.0 / rows
+        ma.per_sample, ma.y_soft, ma.pred_class = self.moe_ps.data_ptr(), self.moe_ysoft.data_ptr(), self.moe_cls.data_ptr()
+        ma.d_pred, ma.dpred_dtype = self.moe_dpred.data_ptr(), self.dt
+        ma.ld_dpred, ma.dpred_cols = self.moe_dpred.stride(0), self.moe_dpred.shape[1]
+        ma.d_gate, ma.ld_dgate = self.moe_dgate.data_ptr(), E
+        _abi.check(self.lib.dmvae_moe_fwd_bwd(self.ctx, C.byref(ma), st()))
+        _abi.check(self.lib.dmvae_reduce_columns(self.ctx, self.moe_ps.data_ptr(), 2, rows, 2, 1.0, self.moe_loss.data_ptr(), st()))
+        if not train:
+            return
+        if self.model == "vade":
+            raise NotImplementedError("training the VaDE-gated MoE (gradient of the supervised loss through gamma) is not "
+                                      "implemented yet; dmoe / dvmoe are")
+        # gate gradient through the softmax into the c-head logits (added to the ELBO's own d_logits when lossVAE)
+        _abi.check(self.lib.dmvae_softmax_bwd_add(self.ctx, rows, self.K, self.qc.data_ptr(), self.moe_dgate.data_ptr(), E,
+                                                  self.dch.data_ptr(), self.dt, self.dch.stride(0), 1 if lossVAE else 0,
+                                                  self.dch.shape[1], st()))
+        self._wgrad("moe", a_in, a_in.stride(0), self.moe_dpred, self.moe_dpred.stride(0), rows)
+        dme = None
+        if feat:
+            # d relu(mean): dgrad through the expert weights, masked by relu(mean) > 0, added to d_mean
+            self._dgrad("moe", self.moe_dpred, self.moe_dpred.stride(0), self.moe_in, self.moe_in.stride(0), self.moe_dinp, F32,
+                        rows, self.L, self.moe_dinp.shape[1])
+            dme = self.moe_dinp
+        self.backward(rows, dmean_extra=dme, train_decoder=lossVAE, train_z=lossVAE or feat, train_c=True, train_trunk=True,
+                      through_decoder=lossVAE)
+        self._grads_dirty = True
+        self._join()
+        if opt is not None:
+            self._update(opt)
+            self.step_count += 1
 
     use_graphs = True
 

@@ -190,6 +190,15 @@ int dmvae_moe_fwd_bwd(dmvae_ctx* ctx, const dmvae_moe_args* a, void* stream);
 int dmvae_softmax_bwd_add(dmvae_ctx* ctx, int rows, int K, const float* q, const float* d_gate, int64_t ld_dgate,
                           void* d_logits, int dtype, int64_t ld_dlogits, int accumulate, int cols, void* stream);
 
+/* q = softmax(scores) row-wise (base_models.py:249), fp32 [rows,K] dense output */
+int dmvae_softmax_rows(dmvae_ctx* ctx, const float* scores, int64_t ld, int rows, int K, float* q, void* stream);
+/* out[c] = scale * sum_r src[r,c]  (deterministic batch reductions of per-sample terms) */
+int dmvae_reduce_columns(dmvae_ctx* ctx, const float* src, int64_t ld, int rows, int cols, float scale, float* out, void* stream);
+/* fp32 features [rows,n] -> operand matrix [rows, out_cols] with optional ReLU and the ones column at n
+ * (models.py:58-61: inp2cls = relu(vae.mean) when featLearn) */
+int dmvae_stage_features(dmvae_ctx* ctx, const float* src, int64_t ld, int rows, int n, int relu, void* out, int out_dtype,
+                         int64_t ld_out, int out_cols, void* stream);
+
 /* ---- TF-semantics Adam (tf.train.AdamOptimizer, base_models.py:102-110) ---------------------
  * theta -= lr_t m/(sqrt(v)+eps), lr_t = lr sqrt(1-b2^t)/(1-b1^t) computed by the caller in double.
  * Flat over n fp32 parameters.  Optionally writes the bf16 operand copy and clears the gradient. */
