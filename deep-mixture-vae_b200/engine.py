@@ -12,6 +12,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Tuple
 
@@ -481,9 +482,13 @@ class Engine:
             return 1
         if self.split_k_wgrad is not None:
             return max(1, self.split_k_wgrad)
-        tiles = ((m + 127) // 128) * ((n + 127) // 128)
         nkb = (rows + 63) // 64
         sms = 148
+        if m >= 256 and n >= 128 and os.environ.get("DMVAE_GEMM_PAIR") != "0":
+            # CTA-pair kernel (256 x 256 tiles, persistent): one work unit per SM pair, never more units than pairs
+            tiles = ((m + 255) // 256) * ((n + 255) // 256)
+            return max(1, min(nkb // 2, (sms // 2) // tiles))
+        tiles = ((m + 127) // 128) * ((n + 127) // 128)
         sk = max(1, min(nkb, (2 * sms + tiles - 1) // tiles))
         return sk
 
