@@ -2,6 +2,8 @@
 // input staging, Adam (TF semantics), data-parallel reduce+Adam over peer memory, evaluation helpers.
 #include "common.cuh"
 
+#include <stdlib.h>
+
 static thread_local char g_err[1024] = "";
 
 void dmvae_set_error(const char* fmt, ...) {
@@ -9,6 +11,15 @@ void dmvae_set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+bool dmvae_pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DMVAE_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
 }
 
 extern "C" int dmvae_abi_version(void) { return DMVAE_B200_ABI_VERSION; }
@@ -52,6 +63,8 @@ extern "C" int dmvae_ctx_has_tcgen05(const dmvae_ctx* ctx) {
 // zero / cast
 // ---------------------------------------------------------------------------------------------
 __global__ void zero_f32_kernel(float4* __restrict__ p4, float* __restrict__ tail, int64_t n4, int64_t ntail) {
+  pdl_wait();
+  pdl_launch_dependents();
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (; i < n4; i += stride) p4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -64,12 +77,14 @@ extern "C" int dmvae_zero_f32(dmvae_ctx* ctx, float* p, int64_t n, void* stream)
   if (n == 0) return DMVAE_OK;
   int64_t n4 = n / 4;
   int blocks = (int)min((int64_t)ctx->sm_count * 8, (n4 + 255) / 256 + 1);
-  zero_f32_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((float4*)p, p + n4 * 4, n4, n - n4 * 4);
+  dmvae_launch(zero_f32_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, true, (float4*)p, p + n4 * 4, n4, n - n4 * 4);
   DMVAE_LAUNCH_CHECK(ctx);
   return DMVAE_OK;
 }
 
 __global__ void cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t n) {
+  pdl_wait();
+  pdl_launch_dependents();
   int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;
   int64_t stride = (int64_t)gridDim.x * blockDim.x * 8;
   for (; i + 8 <= n; i += stride) {
@@ -86,7 +101,7 @@ extern "C" int dmvae_cast_bf16(dmvae_ctx* ctx, const float* src, void* dst, int6
   DMVAE_CHECK_ARG(((uintptr_t)src & 31) == 0 && ((uintptr_t)dst & 15) == 0, "dmvae_cast_bf16: misaligned pointers");
   if (n == 0) return DMVAE_OK;
   int blocks = (int)min((int64_t)ctx->sm_count * 8, (n / 8 + 255) / 256 + 1);
-  cast_bf16_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, (__nv_bfloat16*)dst, n);
+  dmvae_launch(cast_bf16_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, true, src, (__nv_bfloat16*)dst, n);
   DMVAE_LAUNCH_CHECK(ctx);
   return DMVAE_OK;
 }
@@ -97,6 +112,8 @@ extern "C" int dmvae_cast_bf16(dmvae_ctx* ctx, const float* src, void* dst, int6
 template <typename TX, typename TO>
 __global__ void stage_input_kernel(const TX* __restrict__ X, int64_t ldx, TO* __restrict__ A, int64_t lda, int rows,
                                    int D, int vec) {
+  pdl_wait();
+  pdl_launch_dependents();
   // one warp per row; 8 elements per lane per iteration when the row pitches allow vector access
   int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
@@ -130,7 +147,7 @@ extern "C" int dmvae_stage_input(dmvae_ctx* ctx, const void* X, int x_dtype, int
   cudaStream_t s = (cudaStream_t)stream;
   const int vec = (ldx % 8 == 0) && (ld_out % 8 == 0) && (((uintptr_t)X) % (8 * dmvae_dtype_size(x_dtype)) == 0) &&
                   (((uintptr_t)A0) % (8 * dmvae_dtype_size(out_dtype)) == 0);
-#define STAGE(TX, TO) stage_input_kernel<TX, TO><<<blocks, 256, 0, s>>>((const TX*)X, ldx, (TO*)A0, ld_out, rows, D, vec)
+#define STAGE(TX, TO) dmvae_launch(stage_input_kernel<TX, TO>, dim3(blocks), dim3(256), 0, s, true, (const TX*)X, ldx, (TO*)A0, ld_out, rows, D, vec)
   if (x_dtype == DMVAE_F32 && out_dtype == DMVAE_F32) STAGE(float, float);
   else if (x_dtype == DMVAE_F32 && out_dtype == DMVAE_BF16) STAGE(float, __nv_bfloat16);
   else if (x_dtype == DMVAE_U8 && out_dtype == DMVAE_F32) STAGE(uint8_t, float);
@@ -170,6 +187,8 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ params, f
                                                     __nv_bfloat16* __restrict__ pbf, int64_t n4, float lr_t,
                                                     const float* __restrict__ lr_t_dev, float b1, float b2, float eps,
                                                     float gs, int zero_grads) {
+  pdl_wait();
+  pdl_launch_dependents();
   if (lr_t_dev) lr_t = __ldg(lr_t_dev);
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -202,7 +221,7 @@ extern "C" int dmvae_adam(dmvae_ctx* ctx, float* params, float* grads, float* m,
   if (n == 0) return DMVAE_OK;
   int64_t n4 = n / 4;
   int blocks = (int)min((int64_t)ctx->sm_count * 8, (n4 + 255) / 256);
-  adam_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(params, grads, m, v, (__nv_bfloat16*)params_bf16, n4, lr_t,
+  dmvae_launch(adam_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, true, params, grads, m, v, (__nv_bfloat16*)params_bf16, n4, lr_t,
                                                          lr_t_dev, beta1, beta2, eps, grad_scale, zero_grads);
   DMVAE_LAUNCH_CHECK(ctx);
   return DMVAE_OK;
@@ -215,6 +234,8 @@ struct StepState {
   float lr_t;
 };
 __global__ void step_tick_kernel(StepState* st, float lr, float b1, float b2) {
+  pdl_wait();
+  pdl_launch_dependents();
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     st->step += 1ull;
     unsigned int t = st->t + 1u;
@@ -224,7 +245,7 @@ __global__ void step_tick_kernel(StepState* st, float lr, float b1, float b2) {
 }
 extern "C" int dmvae_step_tick(dmvae_ctx* ctx, void* state_dev, float lr, float beta1, float beta2, void* stream) {
   DMVAE_CHECK_ARG(ctx && state_dev, "dmvae_step_tick: NULL argument");
-  step_tick_kernel<<<1, 32, 0, (cudaStream_t)stream>>>((StepState*)state_dev, lr, beta1, beta2);
+  dmvae_launch(step_tick_kernel, dim3(1), dim3(32), 0, (cudaStream_t)stream, true, (StepState*)state_dev, lr, beta1, beta2);
   DMVAE_LAUNCH_CHECK(ctx);
   return DMVAE_OK;
 }

@@ -78,12 +78,43 @@ void dmvae_set_error(const char* fmt, ...);
     (ctx)->launches++;                                                                       \
   } while (0)
 
+// ---------------------------------------------------------------------------------------------
+// programmatic dependent launch (PDL)
+// ---------------------------------------------------------------------------------------------
+// A kernel launched through dmvae_launch(..., pdl=true) may be scheduled while its stream predecessor is still
+// draining (its CTAs become resident as the predecessor's exit, their prologue - barrier init, TMEM allocation,
+// descriptor prefetch, table staging from kernel parameters - overlaps the predecessor's tail and the launch
+// latency disappears).  Such a kernel MUST call pdl_wait() before it reads or writes any global memory the
+// predecessor may touch; pdl_wait() returns once the predecessor grid has completed and its writes are visible.
+// DMVAE_PDL=0 in the environment turns the attribute off (A/B measurements).
+bool dmvae_pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t dmvae_launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl,
+                                       Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (pdl && dmvae_pdl_enabled()) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 static inline size_t dmvae_dtype_size(int dt) { return dt == DMVAE_F32 ? 4 : dt == DMVAE_BF16 ? 2 : 1; }
 
 // ---------------------------------------------------------------------------------------------
 // device helpers
 // ---------------------------------------------------------------------------------------------
 #ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -10,6 +10,10 @@
 // Formulas: SURVEY.md section 8(a'), restated and checked in oracle/closed_form.py.
 #include "common.cuh"
 
+#include <cuda_fp16.h>
+
+#include <stdlib.h>
+
 namespace {
 
 constexpr int kThreads = 256;
@@ -21,6 +25,9 @@ struct ElboParams {
   dmvae_elbo_args a;
   int Ls;          // padded (odd) row stride of the shared prior tables
   int vec_ok;      // 8-wide vector path usable for the streaming part
+  int bulk_ok;     // rows can be moved with 16-byte-granular bulk async copies (row-tile kernel)
+  int xrow, drow;  // bytes per row of the shared-memory target / logits tiles
+  int contig;      // global row pitches equal xrow / drow: whole-tile bulk copies
 };
 
 template <int INPUT>
@@ -50,6 +57,8 @@ __device__ __forceinline__ float recon8(const float (&x)[8], const float (&d)[8]
 template <typename TX, typename TD, int INPUT, int kKPL>
 __global__ void __launch_bounds__(kThreads) elbo_kernel(const ElboParams p) {
   extern __shared__ float smem[];
+  pdl_wait();
+  pdl_launch_dependents();
   const dmvae_elbo_args& a = p.a;
   const int L = a.L, K = a.K, Ls = p.Ls, D = a.D;
   const int mode = a.mode;
@@ -343,6 +352,506 @@ __global__ void __launch_bounds__(kThreads) elbo_kernel(const ElboParams p) {
   }
 }
 
+// ---- shared-memory tile access and bulk async copies (row-tile kernel) ----
+__device__ __forceinline__ uint32_t smem_addr_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_parity(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "EW_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra.uni EW_DONE;\n"
+      "bra.uni EW_LOOP;\n"
+      "EW_DONE:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+
+// 8 consecutive elements of a shared-memory tile <-> 8 floats
+template <typename T>
+struct Tile8;
+template <>
+struct Tile8<float> {
+  static __device__ __forceinline__ void load(uint32_t a, float (&v)[8]) {
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(a));
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "r"(a + 16));
+  }
+  static __device__ __forceinline__ void store(uint32_t a, const float (&v)[8]) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a + 16), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
+  }
+};
+template <>
+struct Tile8<__nv_bfloat16> {
+  static __device__ __forceinline__ void load(uint32_t a, float (&v)[8]) {
+    uint32_t w[4];
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(a));
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      v[2 * i] = __uint_as_float(w[i] << 16);
+      v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+  }
+  static __device__ __forceinline__ void store(uint32_t a, const float (&v)[8]) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+      w[i] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+  }
+};
+template <>
+struct Tile8<uint8_t> {
+  static __device__ __forceinline__ void load(uint32_t a, float (&v)[8]) {
+    uint32_t lo, hi;
+    asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(lo), "=r"(hi) : "r"(a));
+    // byte b -> float bits 0x4B0000bb = 2^23 + b, minus 2^23: exact, full-rate (no I2F on the XU pipe)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      v[i] = __uint_as_float(__byte_perm(lo, 0x4B000000u, 0x7540 + i)) - 8388608.f;
+      v[4 + i] = __uint_as_float(__byte_perm(hi, 0x4B000000u, 0x7540 + i)) - 8388608.f;
+    }
+  }
+};
+
+// =================================================================================================
+// Row-tile kernel for the common small-mixture case (DMVAE analytic KL, K*L small): a CTA owns 32 rows.
+//   warps 0-7 : stream the D-wide reconstruction part, 4 rows per warp treated as ONE list of 8-element chunks
+//               (no per-row tail iteration); every chunk's loads are issued before the first is consumed.
+//   warp  8   : the latent part with lane <-> row (K*L is tiny: one thread walks it serially, so the 32 rows
+//               cost ~K*L warp-instructions instead of ~32 x (shuffles + shared-memory round trips) per row).
+// Same formulas and outputs as elbo_kernel.
+// =================================================================================================
+constexpr int kFastRW = 2;                  // rows per reconstruction warp
+constexpr int kFastRows = 8 * kFastRW;      // rows per CTA
+constexpr int kLatWarps = 2;                // latent warps: 8 rows each, 4 lanes per row
+constexpr int kFastThreads = 32 * (8 + kLatWarps);
+
+// shared-memory plan of the row-tile kernel (floats)
+struct RowTileSmem {
+  int tab_m, tab_iv, sum_plv, mu, lv, q, g, dmu, dlv, R, total;
+  __host__ __device__ RowTileSmem(int L, int K, int Ls, int Ks) {
+    int o = 0;
+    tab_m = o; o += K * Ls;
+    tab_iv = o; o += K * Ls;
+    sum_plv = o; o += (K + 3) & ~3;
+    mu = o; o += kFastRows * Ls;
+    lv = o; o += kFastRows * Ls;            // log_var, then exp(log_var)
+    q = o; o += kFastRows * Ks;             // logits -> q(c|x)
+    g = o; o += kFastRows * Ks;             // G_k -> d_logits
+    dmu = o; o += kFastRows * Ls;
+    dlv = o; o += kFastRows * Ls;
+    R = o; o += kFastRows;
+    total = o;
+  }
+};
+
+// fp32 reconstruction term of one element (fp32 decoder logits: the 1e-4 tier).  log1p(t), t = e^{-|d|} in (0,1],
+// is a degree-7 polynomial (max abs error 2.4e-7) on the FMA pipe instead of lg2 on the XU pipe.
+template <int INPUT>
+__device__ __forceinline__ float recon1_rt(float x, float d, float s, float& g) {
+  if (INPUT == DMVAE_INPUT_BINARY) {
+    float t;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(-1.4426950408889634f * fabsf(d)));
+    float pl = -0.008574675768613815f;
+    pl = fmaf(pl, t, 0.044214192777872086f);
+    pl = fmaf(pl, t, -0.10785368084907532f);
+    pl = fmaf(pl, t, 0.17757023870944977f);
+    pl = fmaf(pl, t, -0.2449961155653f);
+    pl = fmaf(pl, t, 0.3327617645263672f);
+    pl = fmaf(pl, t, -0.49997448921203613f);
+    pl = fmaf(pl, t, 0.9999998211860657f);
+    float inv;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(1.f + t));
+    const float sig = d >= 0.f ? inv : t * inv;
+    g = s * (sig - x);
+    return fmaf(pl, t, fmaf(-d, x, fmaxf(d, 0.f)));             // max(d,0) - d x + log1p(e^{-|d|})   (base_models.py:74-79)
+  } else {
+    const float df = d - x;                                     // base_models.py:80-83
+    g = s * df;
+    return 0.5f * df * df;
+  }
+}
+
+__device__ __forceinline__ uint32_t h2_bits(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
+__device__ __forceinline__ __half2 bits_h2(uint32_t u) { return *reinterpret_cast<__half2*>(&u); }
+
+// 8 targets of a shared-memory tile as 4 half2 pairs
+template <typename T>
+__device__ __forceinline__ void tile8_half2(uint32_t a, __half2 (&xh)[4]) {
+  float v[8];
+  Tile8<T>::load(a, v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) xh[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+}
+template <>
+__device__ __forceinline__ void tile8_half2<uint8_t>(uint32_t a, __half2 (&xh)[4]) {
+  uint32_t lo, hi;
+  asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(lo), "=r"(hi) : "r"(a));
+  // bytes (b0, b1) -> halves 0x64b0, 0x64b1 = 1024 + b exactly; minus 1024: one PRMT + one HADD2 per pair
+  const __half2 k1024 = __float2half2_rn(1024.f);
+  xh[0] = __hsub2(bits_h2(__byte_perm(lo, 0x64646464u, 0x4140)), k1024);
+  xh[1] = __hsub2(bits_h2(__byte_perm(lo, 0x64646464u, 0x4342)), k1024);
+  xh[2] = __hsub2(bits_h2(__byte_perm(hi, 0x64646464u, 0x4140)), k1024);
+  xh[3] = __hsub2(bits_h2(__byte_perm(hi, 0x64646464u, 0x4342)), k1024);
+}
+
+// bf16 tier (bf16 decoder logits in, bf16 gradient out; tolerance 2e-2): packed half2 arithmetic, two elements per
+// issue slot.  e^{-|d|} and tanh are one f16x2 MUFU per pair; log1p(t) = t P4(t).  Simulated against fp64 on
+// N(0,3) logits: per-sample sum within 6e-5 relative, gradient within 4e-4 absolute (below its bf16 rounding).
+// The loss terms are accumulated and the gradient is scaled in fp32 (s = 1/batch underflows fp16).
+template <int INPUT>
+__device__ __forceinline__ float recon8_h2(const __half2 (&xh)[4], const uint32_t (&dw)[4], uint32_t (&gw)[4], float s) {
+  float acc = 0.f;
+  const __half2 zero = __float2half2_rn(0.f), half = __float2half2_rn(0.5f);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __half2 d = __floats2half2_rn(__uint_as_float(dw[i] << 16), __uint_as_float(dw[i] & 0xffff0000u));
+    __half2 loss, gd;
+    if (INPUT == DMVAE_INPUT_BINARY) {
+      uint32_t tw, thw;
+      asm("ex2.approx.f16x2 %0, %1;" : "=r"(tw) : "r"(h2_bits(__hmul2(__habs2(d), __float2half2_rn(-1.4426950408889634f)))));
+      const __half2 t = bits_h2(tw);
+      __half2 pl = __float2half2_rn(0.041551114473448364f);
+      pl = __hfma2(pl, t, __float2half2_rn(-0.15783837660869268f));
+      pl = __hfma2(pl, t, __float2half2_rn(0.30656109993887143f));
+      pl = __hfma2(pl, t, __float2half2_rn(-0.4970308426636867f));
+      pl = __hfma2(pl, t, __float2half2_rn(0.9999449934273393f));
+      loss = __hfma2(pl, t, __hfma2(__hneg2(d), xh[i], __hmax2(d, zero)));
+      asm("tanh.approx.f16x2 %0, %1;" : "=r"(thw) : "r"(h2_bits(__hmul2(d, half))));
+      gd = __hsub2(__hfma2(bits_h2(thw), half, half), xh[i]);   // sigmoid(d) - x
+    } else {
+      gd = __hsub2(d, xh[i]);
+      loss = __hmul2(__hmul2(gd, half), gd);
+    }
+    const float2 lf = __half22float2(loss), gf = __half22float2(gd);
+    acc += lf.x;
+    acc += lf.y;
+    __nv_bfloat162 gb = __floats2bfloat162_rn(gf.x * s, gf.y * s);
+    gw[i] = *reinterpret_cast<uint32_t*>(&gb);
+  }
+  return acc;
+}
+
+template <typename TX, typename TD, int INPUT>
+__global__ void __launch_bounds__(kFastThreads, 3) elbo_rowtile_kernel(const ElboParams p) {
+  extern __shared__ __align__(128) float smem[];
+  constexpr bool FAST = sizeof(TD) == 2;
+  const dmvae_elbo_args& a = p.a;
+  const int L = a.L, K = a.K, Ls = p.Ls, D = a.D;
+  const int Ks = K | 1;
+  const RowTileSmem sm(L, K, Ls, Ks);
+  float* tab_m = smem + sm.tab_m;             // [K][Ls]
+  float* tab_iv = smem + sm.tab_iv;           // [K][Ls] exp(-plv)
+  float* sum_plv = smem + sm.sum_plv;         // [K]
+  float* R_s = smem + sm.R;                   // [rows]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row0 = blockIdx.x * kFastRows;
+  const int nrows_cta = min(kFastRows, a.rows - row0);
+  pdl_wait();                                   // everything below reads the previous kernels' outputs
+  pdl_launch_dependents();
+  const float r = a.kl_ratio_dev ? __ldg(a.kl_ratio_dev) : a.kl_ratio;
+  const float s = a.inv_global_batch, s_rec = a.inv_global_batch * a.recon_scale;
+
+  if (warp < 8) {
+    // =========================== reconstruction warps ===========================
+    // bulk-load this warp's slab (targets, decoder logits) into shared memory, transform the logits into the
+    // gradient in place, bulk-store the gradient rows.  These warps never wait for the latent warps.
+    uint8_t* tiles = reinterpret_cast<uint8_t*>(smem) + (((size_t)sm.total * 4 + 127) & ~(size_t)127);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(tiles);                      // 8 mbarriers (one per slab)
+    const uint32_t xt = smem_addr_u32(tiles + 128);
+    const uint32_t dt = xt + (uint32_t)(kFastRows * p.xrow);
+    const int rw0 = row0 + warp * kFastRW;
+    const int nrows_w = max(0, min(kFastRW, a.rows - rw0));
+    const uint32_t xt_w = xt + (uint32_t)(warp * kFastRW * p.xrow), dt_w = dt + (uint32_t)(warp * kFastRW * p.drow);
+    // contiguous tiles (row pitch == row bytes) move as ONE bulk copy per tensor and CTA: the TMA unit's cost is per
+    // request (~150 cycles measured), so 48 row-sized copies per CTA had made it the bottleneck
+    const bool whole = p.contig != 0;
+    const uint32_t bar_w = smem_addr_u32(&bars[whole ? 0 : warp]);
+    if (lane == 0 && (!whole || warp == 0)) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_w), "r"(1));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      const uint32_t dbytes = (uint32_t)(D * (int)sizeof(TD));
+      if (whole) {
+        const uint32_t xb = (uint32_t)(nrows_cta * p.xrow), db = (uint32_t)(nrows_cta * p.drow);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_w), "r"(xb + db) : "memory");
+        bulk_g2s(xt, reinterpret_cast<const uint8_t*>(a.X) + (int64_t)row0 * p.xrow, xb, bar_w);
+        bulk_g2s(dt, reinterpret_cast<const uint8_t*>(a.decoded) + (int64_t)row0 * p.drow, db, bar_w);
+      } else {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_w),
+                     "r"((uint32_t)nrows_w * ((uint32_t)p.xrow + dbytes))
+                     : "memory");
+        for (int q = 0; q < nrows_w; ++q) {
+          bulk_g2s(xt_w + (uint32_t)(q * p.xrow),
+                   reinterpret_cast<const uint8_t*>(a.X) + (int64_t)(rw0 + q) * a.ldx * (int64_t)sizeof(TX), (uint32_t)p.xrow, bar_w);
+          bulk_g2s(dt_w + (uint32_t)(q * p.drow),
+                   reinterpret_cast<const uint8_t*>(a.decoded) + (int64_t)(rw0 + q) * a.ld_dec * (int64_t)sizeof(TD), dbytes, bar_w);
+        }
+      }
+    }
+    if (whole) asm volatile("bar.sync 3, 256;" ::: "memory");   // the barrier word is initialised before anyone polls it
+    else __syncwarp();
+    mbar_wait_parity(bar_w, 0);
+    const int cpr = D >> 3;                                     // 8-element chunks per row (D % 8 == 0)
+    const int total = nrows_w * cpr;
+    float racc[kFastRW];
+#pragma unroll
+    for (int q = 0; q < kFastRW; ++q) racc[q] = 0.f;
+    int rr = 0, cc = lane;
+    while (cc >= cpr) { cc -= cpr; ++rr; }
+#pragma unroll 1
+    for (int c = lane; c < total; c += 32) {
+      const uint32_t xa = xt_w + (uint32_t)(rr * p.xrow + cc * 8 * (int)sizeof(TX));
+      const uint32_t da = dt_w + (uint32_t)(rr * p.drow + cc * 8 * (int)sizeof(TD));
+      float v;
+      if (FAST) {
+        __half2 xh[4];
+        uint32_t dw[4], gw[4];
+        tile8_half2<TX>(xa, xh);
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(dw[0]), "=r"(dw[1]), "=r"(dw[2]), "=r"(dw[3]) : "r"(da));
+        v = recon8_h2<INPUT>(xh, dw, gw, s_rec);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(da), "r"(gw[0]), "r"(gw[1]), "r"(gw[2]), "r"(gw[3]) : "memory");
+      } else {
+        float x[8], d[8], g[8];
+        Tile8<TX>::load(xa, x);
+        Tile8<TD>::load(da, d);
+        v = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v += recon1_rt<INPUT>(x[i], d[i], s_rec, g[i]);
+        Tile8<TD>::store(da, g);
+      }
+#pragma unroll
+      for (int q = 0; q < kFastRW; ++q) racc[q] += (rr == q) ? v : 0.f;
+      cc += 32;
+      while (cc >= cpr) { cc -= cpr; ++rr; }
+    }
+    // zero the padding columns [D, ddec_cols) of the gradient rows (operand of the decoder's dgrad / wgrad GEMMs)
+    const int padw = (p.drow - D * (int)sizeof(TD)) >> 2;       // 32-bit words of padding per row
+    for (int i = lane; i < nrows_w * padw; i += 32) {
+      const int r2 = i / padw, j = i - r2 * padw;
+      asm volatile("st.shared.b32 [%0], %1;" ::"r"(dt_w + (uint32_t)(r2 * p.drow + D * (int)sizeof(TD) + 4 * j)), "r"(0u) : "memory");
+    }
+#pragma unroll
+    for (int q = 0; q < kFastRW; ++q) {
+      const float R = warp_sum(racc[q]);
+      if (lane == 0) R_s[warp * kFastRW + q] = R;
+    }
+    asm volatile("bar.arrive 1, %0;" ::"n"(kFastThreads) : "memory");         // R_s written (latent warps wait on it)
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (whole) {
+      asm volatile("bar.sync 3, 256;" ::: "memory");            // every slab of the tile is final
+      if (warp == 0 && lane == 0) {
+        bulk_s2g(reinterpret_cast<uint8_t*>(a.d_decoded) + (int64_t)row0 * p.drow, dt, (uint32_t)(nrows_cta * p.drow));
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      }
+    } else {
+      __syncwarp();
+      if (lane == 0) {
+        for (int q = 0; q < nrows_w; ++q)
+          bulk_s2g(reinterpret_cast<uint8_t*>(a.d_decoded) + (int64_t)(rw0 + q) * a.ld_ddec * (int64_t)sizeof(TD),
+                   dt_w + (uint32_t)(q * p.drow), (uint32_t)p.drow);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");       // the slab is read by the TMA unit until then
+      }
+    }
+    return;
+  }
+
+  // =========================== latent warps: 8 rows each, four lanes per row ===========================
+  float* mu_s = smem + sm.mu;                 // [rows][Ls]
+  float* lv_s = smem + sm.lv;                 // [rows][Ls]
+  float* q_s = smem + sm.q;                   // [rows][Ks]
+  float* g_s = smem + sm.g;                   // [rows][Ks]
+  float* dmu_s = smem + sm.dmu;               // [rows][Ls]
+  float* dlv_s = smem + sm.dlv;               // [rows][Ls]
+  const int lw = warp - 8;
+  const int lt = lw * 32 + lane;                                  // thread index among the latent warps
+  constexpr int kLatThreads = 32 * kLatWarps;
+  constexpr int kRowsPerLat = kFastRows / kLatWarps;              // 8
+  const int lr0 = lw * kRowsPerLat;                               // first tile row of this warp
+  const int nrows_l = max(0, min(kRowsPerLat, nrows_cta - lr0));
+  // stage the prior tables (both latent warps) and this warp's latent inputs; all loads are issued before any use
+  for (int i = lt; i < K * L; i += kLatThreads) {
+    const int k = i / L, l = i - k * L;
+    tab_m[k * Ls + l] = __ldg(a.prior_means + i);
+    tab_iv[k * Ls + l] = expf(-__ldg(a.prior_log_vars + i));
+  }
+  for (int k = lt; k < K; k += kLatThreads) {
+    float sacc = 0.f;
+    for (int l = 0; l < L; ++l) sacc += __ldg(a.prior_log_vars + k * L + l);
+    sum_plv[k] = sacc;
+  }
+  for (int i = lane; i < nrows_l * L; i += 32) {
+    const int rr = i / L, l = i - rr * L;
+    mu_s[(lr0 + rr) * Ls + l] = __ldg(a.mean + (int64_t)(row0 + lr0 + rr) * a.ld_zh + l);
+    lv_s[(lr0 + rr) * Ls + l] = __ldg(a.log_var + (int64_t)(row0 + lr0 + rr) * a.ld_zh + l);
+  }
+  for (int i = lane; i < nrows_l * K; i += 32) {
+    const int rr = i / K, k = i - rr * K;
+    q_s[(lr0 + rr) * Ks + k] = __ldg(a.logits + (int64_t)(row0 + lr0 + rr) * a.ld_logits + k);
+  }
+  asm volatile("bar.sync 2, %0;" ::"n"(kLatThreads) : "memory");              // tables complete (latent warps only)
+
+  const int rl = lr0 + (lane >> 2), h = lane & 3;
+  const bool valid = (lane >> 2) < nrows_l;
+  const int rsel = valid ? rl : lr0;
+  const float logK = logf((float)K);
+  float* mu_r = mu_s + rsel * Ls;
+  float* elv_r = lv_s + rsel * Ls;
+  float* q_r = q_s + rsel * Ks;
+  float* g_r = g_s + rsel * Ks;
+  auto quad_sum = [](float v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    return v;
+  };
+  float sum_lv = 0.f;
+  for (int l = h; l < L; l += 4) {
+    const float lv = elv_r[l];
+    if (valid) elv_r[l] = expf(lv);
+    sum_lv += lv;
+  }
+  sum_lv = quad_sum(sum_lv);
+  float mx = -INFINITY;
+  int amax = K;
+  for (int k = h; k < K; k += 4) {
+    const float sc = q_r[k];
+    if (sc > mx) { mx = sc; amax = k; }                         // first maximum wins
+  }
+#pragma unroll
+  for (int o = 1; o <= 2; o <<= 1) {
+    const float om = __shfl_xor_sync(0xffffffffu, mx, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, amax, o);
+    if (om > mx || (om == mx && oi < amax)) { mx = om; amax = oi; }
+  }
+  float den = 0.f;
+  for (int k = h; k < K; k += 4) {
+    const float e = expf(q_r[k] - mx);
+    if (valid) q_r[k] = e;
+    den += e;
+  }
+  den = quad_sum(den);
+  __syncwarp();                                                 // exp(lv) of all four lanes visible
+  const float inv_den = 1.f / den;
+  float C = 0.f, Zk = 0.f, qG = 0.f;
+  for (int k = h; k < K; k += 4) {
+    const float q = q_r[k] * inv_den;
+    const float* mk = tab_m + k * Ls;
+    const float* ik = tab_iv + k * Ls;
+    float acc = 0.f;
+    for (int l = 0; l < L; ++l) {
+      const float dm = mu_r[l] - mk[l];
+      acc += (elv_r[l] + dm * dm) * ik[l];
+    }
+    const float A = sum_plv[k] - sum_lv - (float)L + acc;
+    const float lq = logf(q + kEps0);
+    C += q * (lq + logK);                                       // priors.py:195-199
+    const float gC = lq + q / (q + kEps0) + logK;
+    const float G = r * (gC + 0.5f * A);
+    Zk += 0.5f * q * A;
+    qG += q * G;
+    if (valid) { q_r[k] = q; g_r[k] = G; }
+  }
+  C = quad_sum(C);
+  Zk = quad_sum(Zk);
+  qG = quad_sum(qG);
+  for (int k = h; k < K; k += 4)
+    if (valid) g_r[k] = s * q_r[k] * (g_r[k] - qG);             // d loss / d logits_k
+  __syncwarp();                                                 // q of all four lanes visible
+  for (int l = h; l < L; l += 4) {
+    const float mu = mu_r[l];
+    float dmu = 0.f, wiv = 0.f, wsum = 0.f;
+    for (int k = 0; k < K; ++k) {
+      const float w = q_r[k], iv = tab_iv[k * Ls + l], mk = tab_m[k * Ls + l];
+      dmu += w * (mu - mk) * iv;
+      wiv += w * iv;
+      wsum += w;
+    }
+    if (valid) {
+      dmu_s[rl * Ls + l] = s * r * dmu;
+      dlv_s[rl * Ls + l] = s * r * 0.5f * (elv_r[l] * wiv - wsum);
+    }
+  }
+  asm volatile("bar.sync 1, %0;" ::"n"(kFastThreads) : "memory");             // every slab's R_s is written
+  if (valid && h == 0) {
+    const float R = R_s[rl];
+    reinterpret_cast<float4*>(a.per_sample)[row0 + rl] = make_float4(R, C, Zk, a.recon_scale * R + r * (C + Zk));
+    a.argmax[row0 + rl] = amax;
+  }
+  __syncwarp();
+  // ---- write-out of this warp's rows ----
+  for (int i = lane; i < nrows_l * K; i += 32) {
+    const int rr = lr0 + i / K, k = i % K;
+    a.qc[(int64_t)(row0 + rr) * K + k] = q_s[rr * Ks + k];
+  }
+  for (int i = lane; i < nrows_l * L; i += 32) {
+    const int rr = lr0 + i / L, l = i % L;
+    a.d_mean_kl[(int64_t)(row0 + rr) * a.ld_dkl + l] = dmu_s[rr * Ls + l];
+    a.d_log_var_kl[(int64_t)(row0 + rr) * a.ld_dkl + l] = dlv_s[rr * Ls + l];
+  }
+  // d_logits rows [K data | zeros to dlogits_cols] in 16-byte pieces
+  if (a.dlogits_dtype == DMVAE_BF16 && (a.dlogits_cols & 7) == 0 && (a.ld_dlogits & 7) == 0) {
+    const int cpr = a.dlogits_cols >> 3;
+    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(a.d_logits);
+    for (int i = lane; i < nrows_l * cpr; i += 32) {
+      const int rr = lr0 + i / cpr, c8 = (i % cpr) << 3;
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = (c8 + j < K) ? g_s[rr * Ks + c8 + j] : 0.f;
+      Vec8<__nv_bfloat16>::store(out + (int64_t)(row0 + rr) * a.ld_dlogits + c8, v);
+    }
+  } else {
+    for (int i = lane; i < nrows_l * a.dlogits_cols; i += 32) {
+      const int rr = lr0 + i / a.dlogits_cols, c = i % a.dlogits_cols;
+      const float v = c < K ? g_s[rr * Ks + c] : 0.f;
+      if (a.dlogits_dtype == DMVAE_BF16)
+        reinterpret_cast<__nv_bfloat16*>(a.d_logits)[(int64_t)(row0 + rr) * a.ld_dlogits + c] = __float2bfloat16_rn(v);
+      else
+        reinterpret_cast<float*>(a.d_logits)[(int64_t)(row0 + rr) * a.ld_dlogits + c] = v;
+    }
+  }
+}
+
+size_t elbo_rowtile_smem_bytes(const ElboParams& p) {
+  const size_t fl = (sizeof(float) * (size_t)RowTileSmem(p.a.L, p.a.K, p.Ls, p.a.K | 1).total + 127) & ~(size_t)127;
+  return fl + 128 + (size_t)kFastRows * (size_t)(p.xrow + p.drow);
+}
+
+bool elbo_rowtile_ok(const ElboParams& p) {
+  static int enabled = -1;                    // DMVAE_ELBO_ROWTILE=0 forces the warp-per-row kernel (A/B measurements)
+  if (enabled < 0) {
+    const char* e = getenv("DMVAE_ELBO_ROWTILE");
+    enabled = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (!enabled) return false;
+  const dmvae_elbo_args& a = p.a;
+  return a.mode == DMVAE_MODE_DMVAE && p.vec_ok && p.bulk_ok && a.K * a.L <= 512 && a.K <= 64 && a.L <= 64 &&
+         ((uintptr_t)a.d_logits & 15) == 0 && elbo_rowtile_smem_bytes(p) <= 100 * 1024;
+}
+
+template <typename TX, typename TD, int INPUT>
+int launch_elbo_rowtile(dmvae_ctx* ctx, const ElboParams& p, cudaStream_t st) {
+  const size_t smem = elbo_rowtile_smem_bytes(p);
+  auto kern = elbo_rowtile_kernel<TX, TD, INPUT>;
+  if (smem > 48 * 1024) DMVAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int blocks = (p.a.rows + kFastRows - 1) / kFastRows;
+  dmvae_launch(kern, dim3(blocks), dim3(kFastThreads), smem, st, true, p);
+  DMVAE_LAUNCH_CHECK(ctx);
+  return DMVAE_OK;
+}
+
 size_t elbo_smem_bytes(int L, int K, int Ls) {
   const int Lp = (L + 3) & ~3, Kp = (K + 3) & ~3;
   return sizeof(float) * (size_t)(2 * K * Ls + Kp + kWarps * (4 * Lp + 2 * Kp));
@@ -357,13 +866,14 @@ int launch_elbo_k(dmvae_ctx* ctx, const ElboParams& p, cudaStream_t st) {
   if (smem > 0) per_sm = (int)min((size_t)8, (size_t)(220 * 1024) / max(smem, (size_t)1));
   if (per_sm < 1) per_sm = 1;
   int blocks = min(ctx->sm_count * per_sm, (p.a.rows + kWarps - 1) / kWarps);
-  kern<<<blocks, kThreads, smem, st>>>(p);
+  dmvae_launch(kern, dim3(blocks), dim3(kThreads), smem, st, true, p);
   DMVAE_LAUNCH_CHECK(ctx);
   return DMVAE_OK;
 }
 
 template <typename TX, typename TD, int INPUT>
 int launch_elbo(dmvae_ctx* ctx, const ElboParams& p, cudaStream_t st) {
+  if (elbo_rowtile_ok(p)) return launch_elbo_rowtile<TX, TD, INPUT>(ctx, p, st);
   if (p.a.K <= 32) return launch_elbo_k<TX, TD, INPUT, 1>(ctx, p, st);
   if (p.a.K <= 64) return launch_elbo_k<TX, TD, INPUT, 2>(ctx, p, st);
   return launch_elbo_k<TX, TD, INPUT, 4>(ctx, p, st);
@@ -404,6 +914,12 @@ extern "C" int dmvae_elbo_fwd_bwd(dmvae_ctx* ctx, const dmvae_elbo_args* a, void
   p.vec_ok = (a->D % 8 == 0) && (a->ldx % 8 == 0) && (a->ld_dec % 8 == 0) && (a->ld_ddec % 8 == 0) &&
              (((uintptr_t)a->X) % (8 * xs) == 0) && (((uintptr_t)a->decoded) % (8 * ds) == 0) &&
              (((uintptr_t)a->d_decoded) % (8 * ds) == 0);
+  p.xrow = (int)(a->D * xs);
+  p.drow = (int)(a->ddec_cols * ds);
+  p.bulk_ok = (a->D * xs) % 16 == 0 && (a->ldx * xs) % 16 == 0 && (a->D * ds) % 16 == 0 && (a->ld_dec * ds) % 16 == 0 &&
+              (a->ddec_cols * ds) % 16 == 0 && (a->ld_ddec * ds) % 16 == 0 && ((uintptr_t)a->X & 15) == 0 &&
+              ((uintptr_t)a->decoded & 15) == 0 && ((uintptr_t)a->d_decoded & 15) == 0 && a->ddec_cols >= a->D;
+  p.contig = (int64_t)(a->ldx * xs) == p.xrow && (int64_t)(a->ld_dec * ds) == p.drow && (int64_t)(a->ld_ddec * ds) == p.drow;
   DMVAE_CHECK_ARG(elbo_smem_bytes(a->L, a->K, p.Ls) <= 220 * 1024, "elbo: K*L = %d too large for the shared prior tables", a->K * a->L);
   cudaStream_t st = (cudaStream_t)stream;
 #define GO(TX, TD)                                                                            \
@@ -442,6 +958,8 @@ inline int reduce_chunk(int L, int K) {
 __global__ void __launch_bounds__(kRedThreads) elbo_reduce_partial_kernel(const dmvae_elbo_args a, int chunk, int G,
                                                                           float* __restrict__ ws) {
   extern __shared__ float sm[];
+  pdl_wait();
+  pdl_launch_dependents();
   const int L = a.L, K = a.K, nF = 2 * L + 1;
   const int g = blockIdx.x, set = blockIdx.y;
   float* w_sm = sm;                 // [chunk][K]
@@ -504,6 +1022,8 @@ __global__ void __launch_bounds__(kRedThreads) elbo_reduce_final_kernel(const dm
                                                                         float* __restrict__ d_means,
                                                                         float* __restrict__ d_log_vars, int accumulate,
                                                                         float* __restrict__ loss_out) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int L = a.L, K = a.K, nF = 2 * L + 1;
   const int nsets = (a.mode == DMVAE_MODE_VADE) ? 2 : 1;
   const size_t set_stride = (size_t)G * (size_t)(K * nF);
@@ -571,10 +1091,10 @@ extern "C" int dmvae_elbo_reduce(dmvae_ctx* ctx, const dmvae_elbo_args* a, float
   if (smem > 48 * 1024)
     DMVAE_CUDA(cudaFuncSetAttribute(elbo_reduce_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaStream_t st = (cudaStream_t)stream;
-  elbo_reduce_partial_kernel<<<dim3(G, nsets), kRedThreads, smem, st>>>(*a, chunk, G, workspace);
+  dmvae_launch(elbo_reduce_partial_kernel, dim3(G, nsets), dim3(kRedThreads), smem, st, true, *a, chunk, G, workspace);
   DMVAE_LAUNCH_CHECK(ctx);
   const int fin_blocks = max(1, (a->K * a->L + kRedThreads - 1) / kRedThreads);
-  elbo_reduce_final_kernel<<<fin_blocks, kRedThreads, 0, st>>>(*a, G, workspace, d_prior_means, d_prior_log_vars,
+  dmvae_launch(elbo_reduce_final_kernel, dim3(fin_blocks), dim3(kRedThreads), 0, st, true, *a, G, workspace, d_prior_means, d_prior_log_vars,
                                                               accumulate, loss_out);
   DMVAE_LAUNCH_CHECK(ctx);
   return DMVAE_OK;

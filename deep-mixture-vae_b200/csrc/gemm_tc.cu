@@ -368,6 +368,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = tmem_slot;
+  pdl_wait();                  // the prologue above overlapped the previous kernel; operands / outputs are touched below
+  pdl_launch_dependents();
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -496,6 +498,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   cluster_sync_all();                     // barriers of both CTAs initialised, TMEM allocated
   tcgen05_fence_after();
   const uint32_t tmem_base = tmem_slot;
+  pdl_wait();                             // the prologue above overlapped the previous kernel's tail
+  pdl_launch_dependents();
 
   // work unit u -> (split, tile); tiles walk M fastest so that concurrently running pairs share B columns
   auto decode = [&](int u, int& m_blk, int& n_blk, int& kb0, int& kb1) {
@@ -676,7 +680,7 @@ int launch_tc(dmvae_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, cons
     smem_opted = smem;
   }
   dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, split);
-  kern<<<grid, kThreads, smem, st>>>(ta, tb, tc, M, N, K, kps, stages, ep);
+  dmvae_launch(kern, grid, dim3(kThreads), smem, st, true, ta, tb, tc, M, N, K, kps, stages, ep);
   DMVAE_LAUNCH_CHECK(ctx);
   return DMVAE_OK;
 }
@@ -698,7 +702,7 @@ int launch_tc2(dmvae_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, con
   }
   const int units = ((M + 2 * BM - 1) / (2 * BM)) * ((N + BN - 1) / BN) * split;
   const int pairs = std::max(1, std::min(units, ctx->sm_count / 2));
-  kern<<<dim3(2 * pairs), kThreads2, P::SMEM, st>>>(ta, tb, tc, M, N, K, kps, split, ep);
+  dmvae_launch(kern, dim3(2 * pairs), dim3(kThreads2), P::SMEM, st, true, ta, tb, tc, M, N, K, kps, split, ep);
   DMVAE_LAUNCH_CHECK(ctx);
   return DMVAE_OK;
 }

@@ -32,6 +32,8 @@ __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& n0, fl
 
 template <typename TZ>
 __global__ void __launch_bounds__(256) reparam_fwd_kernel(const dmvae_reparam_args a) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
   const int L = a.L, K = a.K;
@@ -110,6 +112,8 @@ __global__ void __launch_bounds__(256) reparam_bwd_kernel(int rows, int L, const
                                                            const float* __restrict__ eps, const float* __restrict__ lv,
                                                            int64_t ld_lv, const float* __restrict__ dme, int64_t ld_dme,
                                                            TO* __restrict__ out, int64_t ld_out, int out_cols) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
   for (int row = warp; row < rows; row += nwarps) {
@@ -139,8 +143,8 @@ extern "C" int dmvae_reparam_fwd(dmvae_ctx* ctx, const dmvae_reparam_args* a, vo
   if (a->rows == 0) return DMVAE_OK;
   int blocks = min(ctx->sm_count * 8, (a->rows + 7) / 8);
   cudaStream_t st = (cudaStream_t)stream;
-  if (a->z_dtype == DMVAE_F32) reparam_fwd_kernel<float><<<blocks, 256, 0, st>>>(*a);
-  else if (a->z_dtype == DMVAE_BF16) reparam_fwd_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(*a);
+  if (a->z_dtype == DMVAE_F32) dmvae_launch(reparam_fwd_kernel<float>, dim3(blocks), dim3(256), 0, st, true, *a);
+  else if (a->z_dtype == DMVAE_BF16) dmvae_launch(reparam_fwd_kernel<__nv_bfloat16>, dim3(blocks), dim3(256), 0, st, true, *a);
   else {
     dmvae_set_error("reparam_fwd: z_dtype %d unsupported", a->z_dtype);
     return DMVAE_ERR_INVALID;
@@ -159,10 +163,10 @@ extern "C" int dmvae_reparam_bwd(dmvae_ctx* ctx, int rows, int L, const float* d
   int blocks = min(ctx->sm_count * 8, (rows + 7) / 8);
   cudaStream_t st = (cudaStream_t)stream;
   if (out_dtype == DMVAE_F32)
-    reparam_bwd_kernel<float><<<blocks, 256, 0, st>>>(rows, L, d_mean_kl, d_log_var_kl, ld_kl, dZ, ld_dz, dZ_extra, ld_dze,
+    dmvae_launch(reparam_bwd_kernel<float>, dim3(blocks), dim3(256), 0, st, true, rows, L, d_mean_kl, d_log_var_kl, ld_kl, dZ, ld_dz, dZ_extra, ld_dze,
                                                       eps, log_var, ld_lv, d_mean_extra, ld_dme, (float*)out, ld_out, out_cols);
   else if (out_dtype == DMVAE_BF16)
-    reparam_bwd_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(rows, L, d_mean_kl, d_log_var_kl, ld_kl, dZ, ld_dz, dZ_extra,
+    dmvae_launch(reparam_bwd_kernel<__nv_bfloat16>, dim3(blocks), dim3(256), 0, st, true, rows, L, d_mean_kl, d_log_var_kl, ld_kl, dZ, ld_dz, dZ_extra,
                                                               ld_dze, eps, log_var, ld_lv, d_mean_extra, ld_dme, (__nv_bfloat16*)out, ld_out, out_cols);
   else {
     dmvae_set_error("reparam_bwd: out_dtype %d unsupported", out_dtype);

@@ -235,7 +235,8 @@ def _check_common(got, c, D, tol=1e-4, ps_abs=2e-5):
     assert abs(got["loss"][3] - c["loss"]) < tol * abs(c["loss"])
 
 
-@pytest.mark.parametrize("B,D,L,K", [(256, 784, 10, 10), (37, 12, 3, 4), (130, 3072, 128, 100), (64, 784, 64, 50)])
+@pytest.mark.parametrize("B,D,L,K", [(256, 784, 10, 10), (37, 12, 3, 4), (130, 3072, 128, 100), (64, 784, 64, 50),
+                                     (100, 784, 10, 10), (45, 64, 5, 7), (1, 784, 10, 10), (4096, 784, 10, 10)])
 @pytest.mark.parametrize("binary", [True, False])
 def test_elbo_dmvae_fp32(lib, ctx, B, D, L, K, binary):
     X, dec, mean, lv, logits, eps, m, plv = _elbo_inputs(B, D, L, K, 0, binary)
@@ -259,7 +260,10 @@ def test_elbo_u8_and_bf16_variants(lib, ctx):
     cb = cf.elbo_dmvae(*[a.astype(np.float64) for a in (X, decb, mean, lv, logits, m, plv)])
     got = _run_elbo(lib, ctx, 0, 0, X, dec, mean, lv, logits, None, None, 1.0, m, plv, 1.0, 1.0 / B, x_dtype=2, dec_dtype=1)
     ref_ps = np.stack([cb["R"], cb["C"], cb["Zk"], cb["elbo"]], 1)
-    assert np.all(np.abs(got["per_sample"] - ref_ps) <= 1e-4 * np.abs(ref_ps) + 2e-5)
+    # bf16 tier (north_star tolerance 2e-2): the reconstruction term is evaluated in packed half2 arithmetic;
+    # measured error is ~1e-4, asserted at 1e-3.  The latent terms stay fp32 (1e-4).
+    assert np.all(np.abs(got["per_sample"][:, 1:3] - ref_ps[:, 1:3]) <= 1e-4 * np.abs(ref_ps[:, 1:3]) + 2e-5)
+    assert np.all(np.abs(got["per_sample"] - ref_ps) <= 1e-3 * np.abs(ref_ps) + 2e-5)
     assert relerr(got["d_decoded"][:, :D], cb["d_decoded"]) < 1e-2          # bf16 store
     assert relerr(got["d_logits"][:, :K], cb["d_logits"]) < 1e-2
 
