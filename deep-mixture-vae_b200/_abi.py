@@ -31,6 +31,12 @@ class GemmEpilogue(C.Structure):
                 ("accumulate", c_int32), ("split_k", c_int32)]
 
 
+class ChainGemm(C.Structure):
+    _fields_ = [("trans_a", c_int32), ("trans_b", c_int32), ("A", c_void_p), ("lda", c_int64), ("B", c_void_p),
+                ("ldb", c_int64), ("C", c_void_p), ("ldc", c_int64), ("M", c_int32), ("N", c_int32), ("K", c_int32),
+                ("epi", GemmEpilogue), ("dep", c_int32 * 2), ("dep_all", c_int32 * 2), ("fuse", c_int32)]
+
+
 class ReparamArgs(C.Structure):
     _fields_ = [("rows", c_int32), ("L", c_int32), ("K", c_int32),
                 ("mean", c_void_p), ("log_var", c_void_p), ("ld_zh", c_int64),
@@ -83,6 +89,8 @@ SIGNATURES = {
     "dmvae_ctx_has_tcgen05": (c_int, [c_void_p]),
     "dmvae_gemm": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64,
                            c_int, c_int, c_int, C.POINTER(GemmEpilogue), c_void_p]),
+    "dmvae_gemm_chain_counters": (c_int64, [c_int, c_int]),
+    "dmvae_gemm_chain": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int64, c_int, c_void_p, c_void_p]),
     "dmvae_linear_fwd": (c_int, [c_void_p, c_int, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int,
                                  c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "dmvae_linear_dgrad": (c_int, [c_void_p, c_int, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64,
@@ -109,7 +117,7 @@ SIGNATURES = {
                                          c_void_p, c_void_p]),
     "dmvae_dp_reduce_adam": (c_int, [c_void_p, c_int, c_int, C.POINTER(c_void_p), C.POINTER(c_void_p),
                                      C.POINTER(c_void_p), c_void_p, c_void_p, c_int64, c_int64, c_int64, c_float, c_void_p,
-                                     c_float, c_float, c_float, c_void_p]),
+                                     c_float, c_float, c_float, c_int, c_void_p]),
     "dmvae_zero_f32": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "dmvae_cast_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
 }

@@ -264,7 +264,7 @@ struct DpPeers {
 __global__ void __launch_bounds__(256) dp_reduce_adam_kernel(DpPeers peers, int rank, int world, float* __restrict__ m,
                                                               float* __restrict__ v, int64_t begin4, int64_t end4,
                                                               float lr_t, const float* __restrict__ lr_t_dev, float b1,
-                                                              float b2, float eps) {
+                                                              float b2, float eps, int clear_grads) {
   if (lr_t_dev) lr_t = __ldg(lr_t_dev);
   int64_t i = begin4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -276,8 +276,10 @@ __global__ void __launch_bounds__(256) dp_reduce_adam_kernel(DpPeers peers, int 
       g.x += t.x; g.y += t.y; g.z += t.z; g.w += t.w;
     }
     // this rank is the only reader of element i of every replica's gradient: clear it for the next step's
-    // split-K accumulation
-    for (int r = 0; r < world; ++r) reinterpret_cast<float4*>(peers.grads[r])[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    // split-K accumulation (or leave that to a local pass of each rank after the closing barrier: 7/8 of these
+    // stores cross NVLink)
+    if (clear_grads)
+      for (int r = 0; r < world; ++r) reinterpret_cast<float4*>(peers.grads[r])[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     float4 p = reinterpret_cast<float4*>(peers.params[rank])[i];
     const int64_t li = i - begin4;
     float4 mm = reinterpret_cast<float4*>(m)[li];
@@ -288,7 +290,7 @@ __global__ void __launch_bounds__(256) dp_reduce_adam_kernel(DpPeers peers, int 
     __nv_bfloat162 lo = __floats2bfloat162_rn(p.x, p.y), hi = __floats2bfloat162_rn(p.z, p.w);
     uint2 w = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
     for (int r = 0; r < world; ++r) {
-      reinterpret_cast<float4*>(peers.params[r])[i] = p;
+      if (peers.params[r]) reinterpret_cast<float4*>(peers.params[r])[i] = p;    // NULL: fp32 master kept by its owner only
       if (peers.pbf[r]) reinterpret_cast<uint2*>(peers.pbf[r])[i] = w;
     }
   }
@@ -297,7 +299,8 @@ __global__ void __launch_bounds__(256) dp_reduce_adam_kernel(DpPeers peers, int 
 extern "C" int dmvae_dp_reduce_adam(dmvae_ctx* ctx, int rank, int world, float* const* grads_peers_host,
                                     float* const* params_peers_host, void* const* params_bf16_peers_host, float* m,
                                     float* v, int64_t n, int64_t shard_begin, int64_t shard_end, float lr_t,
-                                    const float* lr_t_dev, float beta1, float beta2, float eps, void* stream) {
+                                    const float* lr_t_dev, float beta1, float beta2, float eps, int clear_grads,
+                                    void* stream) {
   DMVAE_CHECK_ARG(ctx && grads_peers_host && params_peers_host && m && v, "dmvae_dp_reduce_adam: NULL pointer");
   DMVAE_CHECK_ARG(world >= 1 && world <= 8 && rank >= 0 && rank < world, "dmvae_dp_reduce_adam: world %d rank %d", world, rank);
   DMVAE_CHECK_ARG(shard_begin % 4 == 0 && shard_end % 4 == 0 && 0 <= shard_begin && shard_begin <= shard_end && shard_end <= n,
@@ -309,13 +312,14 @@ extern "C" int dmvae_dp_reduce_adam(dmvae_ctx* ctx, int rank, int world, float* 
     peers.grads[r] = grads_peers_host[r];
     peers.params[r] = params_peers_host[r];
     peers.pbf[r] = params_bf16_peers_host ? (__nv_bfloat16*)params_bf16_peers_host[r] : nullptr;
-    DMVAE_CHECK_ARG(peers.grads[r] && peers.params[r], "dmvae_dp_reduce_adam: peer %d pointer is NULL", r);
+    DMVAE_CHECK_ARG(peers.grads[r] && (peers.params[r] || (r != rank && peers.pbf[r])),
+                    "dmvae_dp_reduce_adam: peer %d: gradient pointer, and fp32 or bf16 parameter pointer, required", r);
   }
   if (shard_end == shard_begin) return DMVAE_OK;
   int64_t n4 = (shard_end - shard_begin) / 4;
   int blocks = (int)min((int64_t)ctx->sm_count * 8, (n4 + 255) / 256);
   dp_reduce_adam_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(peers, rank, world, m, v, shard_begin / 4, shard_end / 4,
-                                                                   lr_t, lr_t_dev, beta1, beta2, eps);
+                                                                   lr_t, lr_t_dev, beta1, beta2, eps, clear_grads);
   DMVAE_LAUNCH_CHECK(ctx);
   return DMVAE_OK;
 }

@@ -87,6 +87,8 @@ class DataParallel:
         engine.dp = self
         self.mode = mode
         self.hdl = None
+        self.master_sharded = False
+        self._master_stale = False
         if mode in ("auto", "p2p"):
             try:
                 self._setup_symmetric()
@@ -128,8 +130,12 @@ class DataParallel:
         ptrs = [int(p) for p in hdl.buffer_ptrs]
         VP = C.c_void_p * self.world
         self._g_ptrs = VP(*[p + 4 * P for p in ptrs])
-        self._p_ptrs = VP(*[p for p in ptrs])
+        # bf16 tier: the GEMMs only read the bf16 operand copy, so only that is written into every replica; the fp32
+        # master of a shard stays with its owner (Adam's only reader) and is fetched on demand (gather_master)
+        self.master_sharded = eng.params_op is not None
+        self._p_ptrs = VP(*[(p if (r == self.rank or not self.master_sharded) else None) for r, p in enumerate(ptrs)])
         self._b_ptrs = VP(*[(p + 8 * P) if eng.params_op is not None else 0 for p in ptrs])
+        self._master_stale = False
 
     def _opt_shard_state(self, opt):
         """Adam slots of the owned shard only (the other ranks own the rest)."""
@@ -152,14 +158,40 @@ class DataParallel:
             self.hdl.barrier(channel=0)                   # every rank's gradients are complete
             abi.check(eng.lib.dmvae_dp_reduce_adam(eng.ctx, self.rank, self.world, self._g_ptrs, self._p_ptrs,
                                                    self._b_ptrs, m.data_ptr(), v.data_ptr(), eng.n_params, b, e, lr_t,
-                                                   lr_dev, opt.beta1, opt.beta2, opt.eps, eng._stream()))
-            self.hdl.barrier(channel=1)                   # every replica updated, every gradient shard cleared
+                                                   lr_dev, opt.beta1, opt.beta2, opt.eps, 0, eng._stream()))
+            self.hdl.barrier(channel=1)                   # every replica updated, every gradient shard consumed
+            # clear the local gradient buffer (split-K accumulates into it): local HBM instead of 7/8 remote stores
+            abi.check(eng.lib.dmvae_zero_f32(eng.ctx, eng.grads.data_ptr(), eng.n_params, eng._stream()))
+            self._master_stale = self.master_sharded
         else:
             dist.all_reduce(eng.grads, op=dist.ReduceOp.SUM, group=self.group)
             abi.check(eng.lib.dmvae_adam(eng.ctx, eng.params.data_ptr(), eng.grads.data_ptr(), opt.m.data_ptr(),
                                          opt.v.data_ptr(), eng.params_op.data_ptr() if eng.params_op is not None else None,
                                          eng.n_params, lr_t, lr_dev, opt.beta1, opt.beta2, opt.eps, 1.0, 1, eng._stream()))
         eng._grads_dirty = False
+
+    def mark_updated(self):
+        """Called once per optimisation step (also for CUDA-graph replays, where update() itself does not run)."""
+        self._master_stale = self.master_sharded
+
+    def gather_master(self):
+        """Fetch the other ranks' fp32 master shards into this rank's parameter buffer (one-sided reads of the peers'
+        symmetric memory; no collective, so a single rank may call it - e.g. rank 0 writing a checkpoint - as long as the
+        ranks are between steps)."""
+        if not getattr(self, "_master_stale", False) or self.hdl is None:
+            return
+        eng = self.eng
+        torch.cuda.current_stream(eng.device).synchronize()
+        n = eng.n_params
+        for r in range(self.world):
+            if r == self.rank:
+                continue
+            b, e = shard_range(n, r, self.world)
+            if e > b:
+                peer = self.hdl.get_buffer(r, (n,), torch.float32, 0)
+                eng.params[b:e].copy_(peer[b:e])
+        torch.cuda.current_stream(eng.device).synchronize()
+        self._master_stale = False
 
     def train_step(self, X, rows, opt, kl_ratio=1.0):
         self.eng.train_step(X, rows, opt, kl_ratio=kl_ratio)

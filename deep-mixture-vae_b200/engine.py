@@ -276,6 +276,8 @@ class Engine:
     def get_variable(self, name: str, grad: bool = False) -> np.ndarray:
         if name in self.dead_vars:
             return self.dead_values[name].copy()
+        if self.dp is not None and not grad:
+            self.dp.gather_master()            # data parallel, bf16 tier: fp32 master shards live on their owners
         vv = self.vars[name]
         t = self._view(vv, grad).detach().cpu().numpy()
         if vv.transform == "moe_w":          # storage [I, E*O] -> reference [E, O, I]
@@ -568,6 +570,82 @@ class Engine:
             a = self.act[nm]
         self._fwd("decx", a, a.stride(0), self.decoded, self.dec_dt, _abi.ACT_NONE, rows)
 
+    # ------------------------------------------------------------------------------------------
+    # chained forward: encoder -> heads (+ fused reparameterisation) -> decoder in ONE persistent launch
+    # ------------------------------------------------------------------------------------------
+    # off by default: measured on B200 (scripts/chain_bench.py) the chained forward is bit-identical but slower than
+    # one launch per layer (115 vs 95 us at 4096 rows): the per-layer hand-off through global memory (TMA-store
+    # completion -> release counter -> acquire -> TMA load) costs about as much as a PDL kernel boundary and is paid
+    # on every row block's 9-layer critical path.  DMVAE_CHAIN=1 turns it on.
+    use_chain = os.environ.get("DMVAE_CHAIN", "0") == "1"
+
+    def _chain_ok(self, gumbel_injected: bool) -> bool:
+        return (self.use_chain and self.dt == BF16 and self.timers is None and 2 * self.L <= 32
+                and not (self.model == "dmvae" and self.cluster_sample) and not gumbel_injected)
+
+    def _chain_entry(self, name, A, lda, C, ldc, out_dt, act, rows, dep=-1, fuse=0, n=None, k=None, W=None, ldw=None):
+        ly = self.layers[name]
+        g = _abi.ChainGemm()
+        g.trans_a, g.trans_b = 0, 0
+        Wt = self.W(name, op=True) if W is None else W
+        g.A, g.lda = A.data_ptr(), lda
+        g.B, g.ldb = Wt.data_ptr(), ly.out_pad if ldw is None else ldw
+        g.C, g.ldc = C.data_ptr(), ldc
+        g.M, g.N, g.K = rows, ly.out_pad if n is None else n, ly.in_pad if k is None else k
+        g.epi.out_dtype, g.epi.act = out_dt, act
+        g.epi.n_valid, g.epi.n_block = ly.n_valid, ly.n_block if ly.n_block > 0 else g.N
+        g.epi.pad_one, g.epi.split_k = 1.0, 1
+        g.dep[0], g.dep[1] = dep, -1
+        g.fuse = fuse
+        return g
+
+    def _run_chain(self, entries, rows, ra=None, zero=True):
+        n = len(entries)
+        need = int(self.lib.dmvae_gemm_chain_counters(n, max(rows, self.max_rows)))
+        if getattr(self, "_chain_cnt", None) is None or self._chain_cnt.numel() < need:
+            self._chain_cnt = torch.zeros(need, dtype=torch.int32, device=self.device)
+        arr = (_abi.ChainGemm * n)(*entries)
+        _abi.check(self.lib.dmvae_gemm_chain(self.ctx, arr, n, self._chain_cnt.data_ptr(), self._chain_cnt.numel(),
+                                             1 if zero else 0, C.byref(ra) if ra is not None else None, self._stream()))
+
+    def forward_chain(self, rows: int, eps_injected: bool, row_offset: int = 0, step: Optional[int] = None,
+                      step_dev: Optional[int] = None):
+        """encode + reparam + decode (base_models.py:218-293) as one dmvae_gemm_chain launch."""
+        relu, none = _abi.ACT_RELU, _abi.ACT_NONE
+        ent, idx = [], {}
+        a, prev = self.act["x"], -1
+        for nm in self.enc_chain:
+            ent.append(self._chain_entry(nm, a, a.stride(0), self.act[nm], self.act[nm].stride(0), self.dt, relu, rows, prev))
+            prev = len(ent) - 1
+            a = self.act[nm]
+        if self.model == "dmvae":
+            h = self.act["ench"]
+            hp = self.layers["ench"].n_block
+            ent.append(self._chain_entry("ench", a, a.stride(0), h, h.stride(0), self.dt, relu, rows, prev))
+            ih = len(ent) - 1
+            ent.append(self._chain_entry("zh", h, h.stride(0), self.zh, self.zh.stride(0), F32, none, rows, ih, fuse=1))
+            iz = len(ent) - 1
+            ent.append(self._chain_entry("ch", h[:, hp:], h.stride(0), self.ch, self.ch.stride(0), F32, none, rows, ih))
+        else:
+            ent.append(self._chain_entry("zh", a, a.stride(0), self.zh, self.zh.stride(0), F32, none, rows, prev, fuse=1))
+            iz = len(ent) - 1
+        a, prev = self.zb, iz
+        for nm in self.dec_chain:
+            ent.append(self._chain_entry(nm, a, a.stride(0), self.act[nm], self.act[nm].stride(0), self.dt, relu, rows, prev))
+            prev = len(ent) - 1
+            a = self.act[nm]
+        ent.append(self._chain_entry("decx", a, a.stride(0), self.decoded, self.decoded.stride(0), self.dec_dt, none, rows, prev))
+        ra = _abi.ReparamArgs()
+        ra.step_dev = step_dev
+        ra.rows, ra.L, ra.K = rows, self.L, self.K
+        ra.mean, ra.log_var, ra.ld_zh = self.zh.data_ptr(), self.zh.data_ptr() + 4 * self.L, self.zh.stride(0)
+        ra.eps_in = self.eps_in.data_ptr() if eps_injected else None
+        ra.seed, ra.step, ra.row_offset = self.noise_seed, self.step_count if step is None else step, row_offset
+        ra.tau = self.temperature
+        ra.Z_out, ra.z_dtype, ra.ld_z, ra.z_cols = self.zb.data_ptr(), self.dt, self.zb.stride(0), self.zb.shape[1]
+        ra.eps_out = self.eps.data_ptr()
+        self._run_chain(ent, rows, ra)
+
     def _elbo_args(self, X, xdt, rows, kl_ratio, inv_global_batch, recon_scale=1.0, klr_dev=None) -> _abi.ElboArgs:
         ea = _abi.ElboArgs()
         ea.kl_ratio_dev = klr_dev
@@ -741,10 +819,13 @@ class Engine:
             if gumbel is not None:
                 self.gumbel_in[:rows].copy_(gumbel.reshape(rows, self.K))
         X, xdt = self.stage_input(X, rows)
-        self.encode(rows)
-        self.reparam(rows, eps is not None, gumbel is not None, row_offset,
-                     step_dev=dev_state.state_dev.data_ptr() if dev_state is not None else None)
-        self.decode(rows)
+        sdev = dev_state.state_dev.data_ptr() if dev_state is not None else None
+        if self._chain_ok(gumbel is not None):
+            self.forward_chain(rows, eps is not None, row_offset, step_dev=sdev)
+        else:
+            self.encode(rows)
+            self.reparam(rows, eps is not None, gumbel is not None, row_offset, step_dev=sdev)
+            self.decode(rows)
         flags = dict(all=(True, True, True, True), vae=(True, True, False, True), prior=(False, False, True, False))[mode]
         klr_dev = self.klr_dev.data_ptr() if (dev_state is not None and mode == "all") else None
         self.elbo(X, xdt, rows, kl_ratio, inv_global_batch, recon_scale, prior_grads=(mode == "all"), klr_dev=klr_dev)
@@ -846,6 +927,8 @@ class Engine:
         self.forward_backward(X, rows, eps, gumbel, kl_ratio, inv, off, recon_scale, True, mode)
         self._update(opt)
         self.step_count += 1
+        if self.dp is not None:
+            self.dp.mark_updated()
 
     def _dp_scale(self, rows):
         """(1 / global batch, global index of this rank's first row): data-parallel shards."""
@@ -881,6 +964,8 @@ class Engine:
             n_nodes = int(self.lib.dmvae_ctx_launch_count(self.ctx)) - l0
             self._graphs[key] = (g, n_nodes)
             self._grads_dirty = False
+            if self.dp is not None:
+                self.dp.mark_updated()
             return
         g, n_nodes = ent
         if getattr(self, "_params_dirty", False):
@@ -893,6 +978,8 @@ class Engine:
             self.klr_dev.fill_(float(kl_ratio))
             self._klr_host = float(kl_ratio)
         g.replay()
+        if self.dp is not None:
+            self.dp.mark_updated()
         opt.t += 1                     # host mirrors of the device counters
         self.step_count += 1
         self._graph_replay_launches += n_nodes

@@ -130,6 +130,34 @@ int dmvae_reparam_bwd(dmvae_ctx* ctx, int rows, int L, const float* d_mean_kl, c
                       const float* d_mean_extra, int64_t ld_dme,
                       void* out, int out_dtype, int64_t ld_out, int out_cols, void* stream);
 
+/* ---- a chain of dependent dense-layer GEMMs in ONE persistent launch (bf16 tcgen05 only) ---------
+ * The layers of one pass (base_models.py:218-293 forward, or the data-gradient / weight-gradient GEMMs of its
+ * autodiff) are walked as one work list by persistent CTA pairs; a tile of layer e starts as soon as the 256-row
+ * block(s) of the earlier layers it reads are complete (per-row-block counters in `counters`), so consecutive
+ * layers overlap and there is one launch instead of one per layer.  Results are identical to calling dmvae_gemm
+ * per entry in order.  dep[d] names an EARLIER entry whose output C this entry reads (as A, B or ReLU mask), -1 for
+ * none; dep_all[d] = 1 when every row block of that output is needed (operands reduced over rows: weight
+ * gradients), 0 when only the rows of the tile itself are (A operand / mask of a same-M layer).
+ * fuse = 1 on the latent head entry (fp32 output [mean | log_var], 2L <= 32) applies dmvae_reparam_fwd's Gaussian
+ * part in the epilogue (arguments in `reparam`; mean / log_var / ld_zh of it are ignored). */
+typedef struct dmvae_chain_gemm {
+  int32_t trans_a, trans_b;
+  const void* A; int64_t lda;
+  const void* B; int64_t ldb;
+  void* C; int64_t ldc;
+  int32_t M, N, K;
+  dmvae_gemm_epilogue epi;
+  int32_t dep[2];
+  int32_t dep_all[2];
+  int32_t fuse;
+} dmvae_chain_gemm;
+/* number of int32 counters a chain of n entries over at most max_rows rows needs */
+int64_t dmvae_gemm_chain_counters(int n, int max_rows);
+/* zero_counters = 1: the call clears the counters itself (a memset node before the kernel); 0: the caller
+ * guarantees they are zero when the kernel starts (e.g. cleared once per step for all chains). */
+int dmvae_gemm_chain(dmvae_ctx* ctx, const dmvae_chain_gemm* g, int n, int32_t* counters, int64_t counters_len,
+                     int zero_counters, const dmvae_reparam_args* reparam, void* stream);
+
 /* ---- fused ELBO forward + backward ------------------------------------------------------------
  * replaces define_recon_loss (base_models.py:72-85), DiscreteFactorial.kl_from_prior
  * (priors.py:183-201), NormalMixtureFactorial.kl_from_prior (priors.py:104-147), get_cluster_probs
@@ -221,7 +249,11 @@ int dmvae_argmax_contingency(dmvae_ctx* ctx, const float* scores, int64_t ld, in
 int dmvae_dp_reduce_adam(dmvae_ctx* ctx, int rank, int world, float* const* grads_peers_host,
                          float* const* params_peers_host, void* const* params_bf16_peers_host,
                          float* m, float* v, int64_t n, int64_t shard_begin, int64_t shard_end,
-                         float lr_t, const float* lr_t_dev, float beta1, float beta2, float eps, void* stream);
+                         float lr_t, const float* lr_t_dev, float beta1, float beta2, float eps,
+                         int clear_grads /* 0: every rank clears its own gradient buffer after the closing barrier */,
+                         void* stream);
+/* params_peers_host[r] may be NULL for r != rank when params_bf16_peers_host[r] is given: the fp32 master copy of a
+ * shard then lives on its owner only (the bf16 operand copy, which is all the GEMMs read, is still replicated). */
 /* zero a fp32 buffer (gradient accumulators) */
 int dmvae_zero_f32(dmvae_ctx* ctx, float* p, int64_t n, void* stream);
 /* fp32 -> bf16 copy (operand copy of the parameters) */

@@ -73,7 +73,30 @@ def main():
             import gc
             gc.collect()
             torch.cuda.synchronize()
+    # bf16 tier: the fp32 master copy of every shard lives on its owner only; gather_master() must rebuild the full
+    # parameter vector, and all replicas' bf16 operand copies must be identical after a step
+    eng = make("bf16", Bl)
+    dp = DataParallel(eng, mode="p2p")
+    opt = eng.optimizer("train", 0.002)
+    for i in range(3):
+        dp.train_step(torch.tensor(Xg[i, rank * Bl:(rank + 1) * Bl], device="cuda"), Bl, opt)
+    torch.cuda.synchronize()
+    dist.barrier()
+    names = ["dmvae/encoder_network/dense/kernel", "dmvae/decoder_network/dense/kernel", "dmvae/representation/means"]
+    mine = torch.tensor(np.concatenate([eng.get_variable(n).ravel() for n in names]), device="cuda")
+    ops = eng.params_op.float().clone()
+    gathered = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(gathered, mine)
+    gops = [torch.zeros_like(ops) for _ in range(world)]
+    dist.all_gather(gops, ops)
+    same = all(torch.equal(gathered[0], g) for g in gathered) and all(torch.equal(gops[0], g) for g in gops)
+    cast_ok = torch.equal(eng.params.to(torch.bfloat16).float(), ops)       # full master (after the gather) == operand copy
+    moved = float((mine - torch.tensor(np.concatenate([make("bf16", Bl).get_variable(n).ravel() for n in names]), device="cuda")).abs().max())
+    good = bool(same and cast_ok and dp.master_sharded and moved > 1e-4)
+    ok = ok and good
     if rank == 0:
+        print("bf16 sharded master: replicas identical %s, master==operand copy %s, parameters moved %.2e -> %s" %
+              (same, cast_ok, moved, "OK" if good else "MISMATCH"), flush=True)
         print("DP_CHECK", "PASS" if ok else "FAIL", flush=True)
     dist.destroy_process_group()
 

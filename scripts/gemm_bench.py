@@ -24,22 +24,20 @@ LAYERS = [("enc1", 832, 512), ("enc2", 512, 512), ("ench", 512, 4096), ("zh", 20
           ("dec1", 64, 2048), ("dec2", 2048, 512), ("dec3", 512, 512), ("decx", 512, 832)]
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--rows", type=int, default=4096)
-    ap.add_argument("--iters", type=int, default=30)
-    ap.add_argument("--check", action="store_true")
-    ap.add_argument("--only", default="")
-    args = ap.parse_args()
-    lib = _abi.load()
-    ctx = C.c_void_p()
-    _abi.check(lib.dmvae_ctx_create(0, C.byref(ctx)))
-    dev = torch.device("cuda", 0)
+def time_gemms(lib, ctx, rows=4096, iters=30, check=False, only="", dev=None, verbose=True):
+    """Device time of every GEMM of one training step (27 launches at cfg2), each as a CUDA-graph replay of `iters`
+    back-to-back launches.  Returns (sum of us per step, padded FLOP per step, worst relative error or nan)."""
+    class _A:
+        pass
+    args = _A()
+    args.rows, args.iters, args.check, args.only = rows, iters, check, only
+    dev = torch.device("cuda", torch.cuda.current_device()) if dev is None else dev
     torch.manual_seed(0)
     B = args.rows
+    _print = print if verbose else (lambda *a, **k: None)
     st = lambda: C.c_void_p(torch.cuda.current_stream().cuda_stream)
     total_us, total_flop, worst = 0.0, 0.0, 0.0
-    print("%-12s %-6s %6s %6s %6s %5s %9s %9s %10s" % ("layer", "pass", "M", "N", "K", "split", "us", "TFLOP/s", "max_err"))
+    _print("%-12s %-6s %6s %6s %6s %5s %9s %9s %10s" % ("layer", "pass", "M", "N", "K", "split", "us", "TFLOP/s", "max_err"))
     for name, kin, nout in LAYERS:
         if args.only and name not in args.only.split(","):
             continue
@@ -110,9 +108,23 @@ def main():
             flop = 2.0 * M * N * K
             total_us += us
             total_flop += flop
-            print("%-12s %-6s %6d %6d %6d %5d %9.2f %9.1f %10.2e" % (name, kind, M, N, K, e.split_k, us, flop / us * 1e-6, err))
-    print("total %.1f us per step of GEMMs, %.1f TFLOP/s (padded shapes); worst rel err %.2e" %
-          (total_us, total_flop / total_us * 1e-6, worst))
+            _print("%-12s %-6s %6d %6d %6d %5d %9.2f %9.1f %10.2e" % (name, kind, M, N, K, e.split_k, us, flop / us * 1e-6, err))
+    _print("total %.1f us per step of GEMMs, %.1f TFLOP/s (padded shapes); worst rel err %.2e" %
+           (total_us, total_flop / total_us * 1e-6, worst))
+    return total_us, total_flop, worst
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--rows", type=int, default=4096)
+    ap.add_argument("--iters", type=int, default=30)
+    ap.add_argument("--check", action="store_true")
+    ap.add_argument("--only", default="")
+    args = ap.parse_args()
+    lib = _abi.load()
+    ctx = C.c_void_p()
+    _abi.check(lib.dmvae_ctx_create(0, C.byref(ctx)))
+    _, _, worst = time_gemms(lib, ctx, args.rows, args.iters, args.check, args.only)
     if args.check and not (worst < 2e-2):
         print("CHECK FAILED")
         sys.exit(1)

@@ -197,8 +197,10 @@ def test_reference_api_training_reduces_loss():
         model.define_train_step(0.002, 100)
         sess = Session()
         data = Dataset((X, cls), batch_size=100)
-        losses = [model.train_op(sess, data, 1.0) for _ in range(3)]
-        assert np.isfinite(losses).all() and losses[-1] < losses[0] * 0.8, losses
+        # the Dataset reshuffles with an unseeded generator (as the reference's does), so the trajectory varies a little
+        # from run to run: four epochs bring the loss to ~0.35-0.5 of the first epoch's
+        losses = [model.train_op(sess, data, 1.0) for _ in range(4)]
+        assert np.isfinite(losses).all() and losses[-1] < losses[0] * 0.7, losses
         acc = model.get_accuracy(sess, data)
         assert 0.0 <= acc <= 1.0
         # reference-shaped loop (host noise, session.run per batch) gives a finite loss too
@@ -211,3 +213,25 @@ def test_reference_api_training_reduces_loss():
         assert np.isfinite(l2)
         lg = sess.run(model.logits, feed_dict={model.X: X[:50]})
         assert lg.shape == (50, 10)
+
+
+def test_chained_forward_is_bit_identical_to_layered():
+    """dmvae_gemm_chain (one persistent launch for encoder -> heads + fused reparameterisation -> decoder) must give
+    exactly the per-layer launches' results, for full and ragged row counts and for both models."""
+    for model, rows in (("dmvae", 300), ("dmvae", 64), ("vade", 257)):
+        cfg, eng, V = _make(model, "bf16")
+        rs = np.random.RandomState(7)
+        X = torch.tensor((rs.uniform(size=(rows, cfg.input_dim)) < 0.2).astype(np.float32), device="cuda")
+        eps = torch.tensor(rs.randn(rows, cfg.latent_dim).astype(np.float32), device="cuda")
+        for injected in (True, False):
+            outs = []
+            for chained in (False, True):
+                eng.use_chain = chained
+                for t in (eng.decoded, eng.zh, eng.zb, eng.eps):
+                    t.zero_()
+                eng.forward_backward(X, rows, eps if injected else None, backward=False)
+                torch.cuda.synchronize()
+                outs.append([t[:rows].clone() for t in (eng.decoded, eng.zh, eng.zb, eng.eps, eng.per_sample)])
+            for a, b in zip(*outs):
+                assert torch.equal(a, b)
+        eng.close()
