@@ -18,13 +18,14 @@ def rel_l2(got, ref):
     return float(np.linalg.norm(got - ref) / max(np.linalg.norm(ref), 1e-30))
 
 
-def _make(model, gemm_dtype, D=784, L=10, K=10, B=256, cluster_sample=False, seed=0, input_type="binary"):
+def _make(model, gemm_dtype, D=784, L=10, K=10, B=256, cluster_sample=False, seed=0, input_type="binary",
+          trunk=(500, 500), head=2000, decoder=(2000, 500, 500)):
     from dmvae_b200.engine import Engine
     if model == "dmvae":
         cfg = rg.GraphConfig(model="dmvae", input_type=input_type, input_dim=D, latent_dim=L, n_classes=K,
-                             cluster_sample=cluster_sample)
-        eng = Engine(model="dmvae", input_type=input_type, input_dim=D, latent_dim=L, n_classes=K, trunk=(500, 500),
-                     head=2000, decoder=(2000, 500, 500), name="dmvae", gemm_dtype=gemm_dtype, max_rows=B,
+                             cluster_sample=cluster_sample, trunk=trunk, head=head, decoder=decoder)
+        eng = Engine(model="dmvae", input_type=input_type, input_dim=D, latent_dim=L, n_classes=K, trunk=trunk,
+                     head=head, decoder=decoder, name="dmvae", gemm_dtype=gemm_dtype, max_rows=B,
                      cluster_sample=cluster_sample, temperature=0.7)
     else:
         cfg = rg.GraphConfig.vade(input_type=input_type, input_dim=D, latent_dim=L, n_classes=K)
@@ -47,7 +48,7 @@ def _data(B, D, L, K, seed=1, binary=True):
     return X, eps, gum
 
 
-def _compare(cfg, eng, V, X, eps, gum, tol, kl_ratio=1.0, argmax_exact=True, round_fn=None):
+def _compare(cfg, eng, V, X, eps, gum, tol, kl_ratio=1.0, argmax_exact=True, round_fn=None, cap=6e-2, total_tol=None):
     B = len(X)
     out, g = rg.loss_and_grads(cfg, V, X, eps, kl_ratio=kl_ratio, gumbel=gum, temperature=0.7, gemm_round=round_fn)
     Xd = torch.tensor(X, device="cuda")
@@ -94,10 +95,10 @@ def _compare(cfg, eng, V, X, eps, gum, tol, kl_ratio=1.0, argmax_exact=True, rou
             den += np.sum(g[name] ** 2)
             e, e_emu = rel_l2(got, g[name]), rel_l2(gb[name], g[name])
             worst = max(worst, e)
-            assert e < 6e-2, "gradient of %s: rel-L2 err %.3g" % (name, e)
+            assert e < cap, "gradient of %s: rel-L2 err %.3g (emulated-bf16 oracle %.3g)" % (name, e, e_emu)
             assert e < 1.5 * e_emu + 5e-3, "gradient of %s: %.3g vs emulated-bf16 oracle %.3g" % (name, e, e_emu)
         total = float(np.sqrt(num / den))
-        assert total < tol, "whole-gradient rel-L2 err %.3g" % total
+        assert total < (tol if total_tol is None else total_tol), "whole-gradient rel-L2 err %.3g" % total
     return worst
 
 
@@ -135,6 +136,23 @@ def test_vade_bf16_step_matches_oracle():
     cfg, eng, V = _make("vade", "bf16", L=64, K=50, B=512)
     X, eps, gum = _data(512, 784, 64, 50)
     _compare(cfg, eng, V, X, eps, gum, 2e-2, argmax_exact=False)
+    eng.close()
+
+
+def test_dmvae_cifar_shapes_bf16_step_matches_oracle():
+    """BASELINE config 5 shapes (3072-d inputs with soft targets, hidden 2000-2000-4000, K=100, latent 128) at a batch the
+    fp64 oracle finishes in seconds: exercises the wide layers (N = 8192 head block), K*L = 12800 prior tables (the
+    warp-per-row ELBO kernel) and ragged tile edges (rows not a multiple of 128)."""
+    B = 72
+    cfg, eng, V = _make("dmvae", "bf16", D=3072, L=128, K=100, B=B, trunk=(2000, 2000), head=4000, decoder=(4000, 2000, 2000))
+    rs = np.random.RandomState(3)
+    X = (rs.randint(0, 256, size=(B, 3072)) / 255.0).astype(np.float32)         # includes/utils.py:204-210
+    eps = rs.randn(B, 128).astype(np.float32)
+    gum = rg.sample_gumbel(rs, (B, 100)).astype(np.float32)
+    # 72 samples through 4000-wide layers: the bf16 operand rounding alone (emulated-bf16 oracle) moves single weight
+    # tensors by up to ~8 %, so the per-tensor cap is wider here; the binding bar stays "within 1.5x the emulated-bf16
+    # oracle's own distance from fp64" for every tensor, and the per-sample terms / loss stay at 2e-2
+    _compare(cfg, eng, V, X, eps, gum, 2e-2, argmax_exact=False, cap=0.15, total_tol=5e-2)
     eng.close()
 
 
