@@ -33,6 +33,7 @@ struct ChainLayer {
   int dep_need[2];     // counter value of one complete row block of the producer
   int dep_tiles_m[2];
   int fuse;            // 1: fused reparameterisation in the epilogue (latent head)
+  int publish;         // 1: a later layer waits for this one (bump the row-block counters once the stores have landed)
 };
 
 struct ChainParams {
@@ -214,14 +215,16 @@ gemm_chain_kernel(const __grid_constant__ ChainParams P) {
       epilogue_warp(tmem_base + as * CH_BN + ((uint32_t)(q * 32) << 16), half * bnh, (half + 1) * bnh,
                     un.m_blk * 2 * BM + (int)rank * BM + q * 32, un.n_blk * Ly.bn, Ly.M, Ly.N, &Ly.tmC, Ly.ep, un.kb0 == 0,
                     my_stage, lane, lead_tempty0 + as * 8, (Ly.fuse && half == 0) ? &P.ra : nullptr);
-      // publish: this warp's part of the tile is in global memory
-      if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-      __syncwarp();
-      if (Ly.fuse) __threadfence();                             // the fused rows were written with ordinary stores by every lane
-      __syncwarp();
-      if (lane == 0) {
-        __threadfence();
-        asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(P.counters + (size_t)e * P.cstride + un.m_blk) : "memory");
+      if (Ly.publish) {
+        // publish: this warp's part of the tile is in global memory
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        __syncwarp();
+        if (Ly.fuse) __threadfence();                           // the fused rows were written with ordinary stores by every lane
+        __syncwarp();
+        if (lane == 0) {
+          __threadfence();
+          asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(P.counters + (size_t)e * P.cstride + un.m_blk) : "memory");
+        }
       }
     }
   }
@@ -243,7 +246,7 @@ extern "C" int64_t dmvae_gemm_chain_counters(int n, int max_rows) {
 
 extern "C" int dmvae_gemm_chain(dmvae_ctx* ctx, const dmvae_chain_gemm* g, int n, int32_t* counters, int64_t counters_len,
                                 int zero_counters, const dmvae_reparam_args* reparam, void* stream) {
-  DMVAE_CHECK_ARG(ctx && g && counters, "gemm_chain: NULL argument");
+  DMVAE_CHECK_ARG(ctx && g, "gemm_chain: NULL argument");
   DMVAE_CHECK_ARG(n >= 1 && n <= kMaxChain, "gemm_chain: 1..%d layers supported (got %d)", kMaxChain, n);
   if (!dmvae_ctx_has_tcgen05(ctx)) {
     dmvae_set_error("gemm_chain: needs an sm_100 device (found sm_%d%d) - there is no fallback", ctx->cc_major, ctx->cc_minor);
@@ -255,12 +258,15 @@ extern "C" int dmvae_gemm_chain(dmvae_ctx* ctx, const dmvae_chain_gemm* g, int n
   memset(&P, 0, sizeof(P));
   int cstride = 1;
   for (int i = 0; i < n; ++i) cstride = std::max(cstride, (g[i].M + 2 * BM - 1) / (2 * BM));
-  DMVAE_CHECK_ARG((int64_t)n * cstride <= counters_len, "gemm_chain: counters buffer too small (%lld < %lld)",
-                  (long long)counters_len, (long long)n * cstride);
+  bool wants_dep = false;
+  for (int i = 0; i < n; ++i) wants_dep = wants_dep || g[i].dep[0] >= 0 || g[i].dep[1] >= 0;
+  DMVAE_CHECK_ARG(!wants_dep || (counters && (int64_t)n * cstride <= counters_len),
+                  "gemm_chain: counters buffer missing or too small (%lld < %lld)", (long long)counters_len, (long long)n * cstride);
   P.n_layers = n;
   P.cstride = cstride;
   P.counters = counters;
   int units = 0, n_fuse = 0;
+  bool any_dep = false;
   const int pairs_avail = ctx->sm_count / 2;
   for (int i = 0; i < n; ++i) {
     const dmvae_chain_gemm& e = g[i];
@@ -306,6 +312,8 @@ extern "C" int dmvae_gemm_chain(dmvae_ctx* ctx, const dmvae_chain_gemm* g, int n
       DMVAE_CHECK_ARG(pe < i, "gemm_chain[%d]: dependency %d must refer to an earlier layer", i, pe);
       const ChainLayer& Pr = P.L[pe];
       Ly.dep[d] = pe;
+      P.L[pe].publish = 1;
+      any_dep = true;
       Ly.dep_all[d] = (e.dep_all[d] || g[pe].M != e.M) ? 1 : 0;
       Ly.dep_need[d] = Pr.tiles_n * Pr.nsplit * 16;            // 8 epilogue warps x 2 CTAs per unit
       Ly.dep_tiles_m[d] = Pr.tiles_m;
@@ -322,7 +330,9 @@ extern "C" int dmvae_gemm_chain(dmvae_ctx* ctx, const dmvae_chain_gemm* g, int n
   }
   P.n_units = units;
   cudaStream_t st = (cudaStream_t)stream;
-  if (zero_counters) DMVAE_CUDA(cudaMemsetAsync(counters, 0, sizeof(int32_t) * (size_t)n * cstride, st));
+  // a list without dependencies is a plain grouped launch: independent GEMMs share one persistent grid
+  const bool memset_first = zero_counters && any_dep;
+  if (memset_first) DMVAE_CUDA(cudaMemsetAsync(counters, 0, sizeof(int32_t) * (size_t)n * cstride, st));
   static bool opted = false;
   if (!opted) {
     DMVAE_CUDA(cudaFuncSetAttribute(gemm_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CH_SMEM));
@@ -330,7 +340,7 @@ extern "C" int dmvae_gemm_chain(dmvae_ctx* ctx, const dmvae_chain_gemm* g, int n
   }
   // every pair must be resident at once (units wait for one another): never more pairs than the device holds
   const int pairs = std::max(1, std::min(units, pairs_avail));
-  DMVAE_CUDA(dmvae_launch(gemm_chain_kernel, dim3(2 * pairs), dim3(kThreads2), CH_SMEM, st, !zero_counters, P));
+  DMVAE_CUDA(dmvae_launch(gemm_chain_kernel, dim3(2 * pairs), dim3(kThreads2), CH_SMEM, st, !memset_first, P));
   DMVAE_LAUNCH_CHECK(ctx);
   return DMVAE_OK;
 }

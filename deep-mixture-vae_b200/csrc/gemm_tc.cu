@@ -332,7 +332,11 @@ int launch_tc(dmvae_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, cons
   if (kps < 1) kps = 1;
   split = (nkb + kps - 1) / kps;      // every split owns at least one k-block
   if (split < 1) split = 1;
-  int stages = BN == 64 ? 4 : 3;      // two CTAs per SM: one tile's epilogue overlaps the other's main loop
+  // short K: two CTAs per SM (one tile's epilogue overlaps the other's main loop).  Long K with few tiles (the latent
+  // heads: 32 CTAs streaming 2048-deep operands): the CTA is latency bound on its TMA loads, so take the whole SM's
+  // shared memory for stages - bytes in flight / latency is its bandwidth
+  int stages = BN == 64 ? 4 : 3;
+  if (kps >= 12) stages = BN == 64 ? 8 : 6;
   const size_t smem = (size_t)stages * STAGE_BYTES + kEpiBytes + 1024;
   auto kern = gemm_tc_kernel<A_MN, B_MN, BN>;
   static size_t smem_opted = 0;       // per instantiation

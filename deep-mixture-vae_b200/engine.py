@@ -451,10 +451,21 @@ class Engine:
     # ------------------------------------------------------------------------------------------
     # kernel wrappers
     # ------------------------------------------------------------------------------------------
-    def _fwd(self, name, A, lda, Y, out_dt, act, rows, W=None, ldw=None, n_out=None, n_in_pad=None):
+    def _fwd(self, name, A, lda, Y, out_dt, act, rows, W=None, ldw=None, n_out=None, n_in_pad=None, split_k=1):
         ly = self.layers[name]
         Wt = self.W(name, op=True) if W is None else W
         t0 = self._tic("gemm")
+        if split_k > 1:
+            # narrow output, deep reduction (latent heads): k-splits reduce into the pre-zeroed fp32 output
+            e = _abi.GemmEpilogue()
+            e.out_dtype, e.act, e.n_valid, e.n_block, e.pad_one = F32, _abi.ACT_NONE, 1 << 30, 1 << 30, 0.0
+            e.accumulate, e.split_k = 1, split_k
+            _abi.check(self.lib.dmvae_gemm(self.ctx, self.dt, 0, 0, A.data_ptr(), lda, Wt.data_ptr(),
+                                           ly.out_pad if ldw is None else ldw, Y.data_ptr(), Y.stride(0), rows,
+                                           ly.out_pad if n_out is None else n_out,
+                                           ly.in_pad if n_in_pad is None else n_in_pad, C.byref(e), self._stream()))
+            self._toc("gemm", t0)
+            return
         _abi.check(self.lib.dmvae_linear_fwd(self.ctx, self.dt, A.data_ptr(), lda, Wt.data_ptr(),
                                              ly.out_pad if ldw is None else ldw, Y.data_ptr(), Y.stride(0), out_dt, rows,
                                              ly.out_pad if n_out is None else n_out,
@@ -462,7 +473,35 @@ class Engine:
                                              self._stream()))
         self._toc("gemm", t0)
 
+    # ---- grouped backward: the weight-gradient and data-gradient GEMMs that become runnable together go out as ONE
+    #      persistent launch (dmvae_gemm_chain without dependencies) instead of one launch each on two streams: the
+    #      separate launches could not overlap anyway (each CTA pair takes a whole SM pair's shared memory), and every
+    #      launch paid its own prologue and tail.  DMVAE_GROUP=0 restores the launch-per-GEMM schedule. ----
+    use_groups = os.environ.get("DMVAE_GROUP", "1") != "0"
+    _group = None
+
+    def _begin_group(self):
+        self._group = [] if (self.use_groups and self.dt == BF16 and self.timers is None) else None
+
+    def _flush_group(self):
+        g = self._group
+        if not g:
+            return
+        if len(g) == 1:
+            g[0][1]()
+        else:
+            n = len(g)
+            arr = (_abi.ChainGemm * n)(*[e for e, _ in g])
+            _abi.check(self.lib.dmvae_gemm_chain(self.ctx, arr, n, None, 0, 0, None, self._stream()))
+        self._group = []
+
+    def _end_group(self):
+        self._flush_group()
+        self._group = None
+
     def _wgrad(self, name, A, lda, dY, lddy, rows, n_out=None, col0=0, accumulate=None):
+        if self._group is not None:
+            return self._wgrad_now(name, A, lda, dY, lddy, rows, n_out, col0, accumulate)
         self._fork(lambda: self._wgrad_now(name, A, lda, dY, lddy, rows, n_out, col0, accumulate))
 
     def _wgrad_now(self, name, A, lda, dY, lddy, rows, n_out=None, col0=0, accumulate=None):
@@ -473,11 +512,36 @@ class Engine:
         acc = 1 if sk > 1 else 0
         if accumulate is not None:
             acc = accumulate
-        t0 = self._tic("gemm")
-        _abi.check(self.lib.dmvae_linear_wgrad(self.ctx, self.dt, A.data_ptr(), lda, dY.data_ptr(), lddy,
-                                               dW.data_ptr() + 4 * col0, ly.out_pad, rows, ly.in_pad, n_out, acc, sk,
-                                               self._stream()))
-        self._toc("gemm", t0)
+
+        def direct():
+            t0 = self._tic("gemm")
+            _abi.check(self.lib.dmvae_linear_wgrad(self.ctx, self.dt, A.data_ptr(), lda, dY.data_ptr(), lddy,
+                                                   dW.data_ptr() + 4 * col0, ly.out_pad, rows, ly.in_pad, n_out, acc, sk,
+                                                   self._stream()))
+            self._toc("gemm", t0)
+
+        if self._group is None:
+            return direct()
+        g = _abi.ChainGemm()                     # dW[in_pad, n_out] (+)= X[rows, in_pad]^T . dY[rows, n_out]
+        g.trans_a, g.trans_b = 1, 0
+        g.A, g.lda, g.B, g.ldb = A.data_ptr(), lda, dY.data_ptr(), lddy
+        g.C, g.ldc = dW.data_ptr() + 4 * col0, ly.out_pad
+        g.M, g.N, g.K = ly.in_pad, n_out, rows
+        g.epi.out_dtype, g.epi.act, g.epi.n_valid, g.epi.n_block = F32, _abi.ACT_NONE, 1 << 30, 1 << 30
+        g.epi.accumulate, g.epi.split_k = acc, sk
+        g.dep[0], g.dep[1] = -1, -1
+        self._group.append((g, direct))
+
+    def _head_split_k(self, rows) -> int:
+        """k-splits of the narrow latent-head GEMMs (and the decoder's first dgrad): only when the single-CTA tiles of one
+        split leave most SMs idle and the reduction is deep enough to share."""
+        if self.dt != BF16 or self.timers is not None:
+            return 1
+        ctas = (rows + 127) // 128
+        kin = self.layers["zh"].in_pad
+        if ctas * 2 > 148 or kin < 1024:
+            return 1
+        return max(1, min(4, 148 // ctas, kin // 512))
 
     def _pick_split_k(self, rows, m, n) -> int:
         if self.dt != BF16:
@@ -495,18 +559,45 @@ class Engine:
         return sk
 
     def _dgrad(self, name, dY, lddy, act_in, ld_act, dX, out_dt, rows, prev_valid, prev_block, W=None, ldw=None,
-               n_in_pad=None, n_out_pad=None):
+               n_in_pad=None, n_out_pad=None, split_k=1):
         ly = self.layers[name]
         Wt = self.W(name, op=True) if W is None else W
-        t0 = self._tic("gemm")
-        _abi.check(self.lib.dmvae_linear_dgrad(self.ctx, self.dt, dY.data_ptr(), lddy, Wt.data_ptr(),
-                                               ly.out_pad if ldw is None else ldw,
-                                               act_in.data_ptr() if act_in is not None else None, ld_act,
-                                               dX.data_ptr(), dX.stride(0), out_dt, rows,
-                                               ly.in_pad if n_in_pad is None else n_in_pad,
-                                               ly.out_pad if n_out_pad is None else n_out_pad, prev_valid, prev_block,
-                                               self._stream()))
-        self._toc("gemm", t0)
+        n_in = ly.in_pad if n_in_pad is None else n_in_pad
+        n_out = ly.out_pad if n_out_pad is None else n_out_pad
+
+        def entry():
+            g = _abi.ChainGemm()                 # dX[rows, n_in] = (dY[rows, n_out] . W[n_in, n_out]^T) * (act_in > 0)
+            g.trans_a, g.trans_b = 0, 1
+            g.A, g.lda, g.B, g.ldb = dY.data_ptr(), lddy, Wt.data_ptr(), ly.out_pad if ldw is None else ldw
+            g.C, g.ldc = dX.data_ptr(), dX.stride(0)
+            g.M, g.N, g.K = rows, n_in, n_out
+            g.epi.out_dtype, g.epi.act = out_dt, _abi.ACT_NONE
+            g.epi.n_valid, g.epi.n_block = prev_valid, prev_block if prev_block > 0 else n_in
+            g.epi.pad_one = 0.0
+            g.epi.relu_mask, g.epi.ld_mask = (act_in.data_ptr() if act_in is not None else None), ld_act
+            g.epi.accumulate, g.epi.split_k = (1 if split_k > 1 else 0), split_k
+            if split_k > 1:                      # partial sums reduce into the cleared fp32 output: linear epilogue only
+                g.epi.n_valid = g.epi.n_block = 1 << 30
+            g.dep[0], g.dep[1] = -1, -1
+            return g
+
+        def direct():
+            t0 = self._tic("gemm")
+            if split_k > 1:
+                g = entry()
+                _abi.check(self.lib.dmvae_gemm(self.ctx, self.dt, 0, 1, g.A, g.lda, g.B, g.ldb, g.C, g.ldc, g.M, g.N, g.K,
+                                               C.byref(g.epi), self._stream()))
+            else:
+                _abi.check(self.lib.dmvae_linear_dgrad(self.ctx, self.dt, dY.data_ptr(), lddy, Wt.data_ptr(),
+                                                       ly.out_pad if ldw is None else ldw,
+                                                       act_in.data_ptr() if act_in is not None else None, ld_act,
+                                                       dX.data_ptr(), dX.stride(0), out_dt, rows, n_in, n_out, prev_valid,
+                                                       prev_block, self._stream()))
+            self._toc("gemm", t0)
+
+        if self._group is None:
+            return direct()
+        self._group.append((entry(), direct))
 
     # ------------------------------------------------------------------------------------------
     # input staging
@@ -524,6 +615,16 @@ class Engine:
     def encode(self, rows: int, heads=("z", "c")):
         """Encoder trunk and heads (base_models.py:218-249 / :490-513)."""
         a = self.act["x"]
+        # A narrow head (N = 64) over a deep reduction is bound by what ONE SM can pull from L2 (~65 GB/s measured:
+        # 32 CTAs took 12 us); split-K spreads the same bytes over 4x the SMs.  The partial sums reduce into fp32
+        # outputs that are cleared on the side stream while the trunk runs (so is dZ, for the decoder's first dgrad).
+        sk = self._head_split_k(rows)
+        if sk > 1:
+            def clear():
+                for t in (self.zh, self.dz) + ((self.ch,) if self.model == "dmvae" else ()):
+                    _abi.check(self.lib.dmvae_zero_f32(self.ctx, t.data_ptr(), rows * t.stride(0), self._stream()))
+            self._fork(clear)
+            self._dz_cleared = True
         for nm in self.enc_chain:
             self._fwd(nm, a, a.stride(0), self.act[nm], self.dt, _abi.ACT_RELU, rows)
             a = self.act[nm]
@@ -531,15 +632,19 @@ class Engine:
             hp = self.layers["ench"].n_block
             self._fwd("ench", a, a.stride(0), self.act["ench"], self.dt, _abi.ACT_RELU, rows)
             h = self.act["ench"]
+            if sk > 1:
+                self._join()
             if "c" in heads:
                 if "z" in heads:
-                    self._fork(lambda: self._fwd("ch", h[:, hp:], h.stride(0), self.ch, F32, _abi.ACT_NONE, rows))
+                    self._fork(lambda: self._fwd("ch", h[:, hp:], h.stride(0), self.ch, F32, _abi.ACT_NONE, rows, split_k=sk))
                 else:
-                    self._fwd("ch", h[:, hp:], h.stride(0), self.ch, F32, _abi.ACT_NONE, rows)
+                    self._fwd("ch", h[:, hp:], h.stride(0), self.ch, F32, _abi.ACT_NONE, rows, split_k=sk)
             if "z" in heads:
-                self._fwd("zh", h, h.stride(0), self.zh, F32, _abi.ACT_NONE, rows)
+                self._fwd("zh", h, h.stride(0), self.zh, F32, _abi.ACT_NONE, rows, split_k=sk)
         else:
-            self._fwd("zh", a, a.stride(0), self.zh, F32, _abi.ACT_NONE, rows)
+            if sk > 1:
+                self._join()
+            self._fwd("zh", a, a.stride(0), self.zh, F32, _abi.ACT_NONE, rows, split_k=sk)
 
     def reparam(self, rows: int, eps_injected: bool, gumbel_injected: bool, row_offset: int = 0, step: Optional[int] = None,
                 step_dev: Optional[int] = None):
@@ -693,6 +798,7 @@ class Engine:
                  train_c=True, train_trunk=True, through_decoder=True):
         """Gradient GEMMs from d_decoded / d_logits / KL-side gradients back to every parameter."""
         dt = self.dt
+        self._begin_group()
         # ---- decoder ----
         chain = self.dec_chain
         a_last = self.act[chain[-1]]
@@ -702,6 +808,7 @@ class Engine:
             ly_prev = self.layers[chain[-1]]
             self._dgrad("decx", self.ddecoded, self.ddecoded.stride(0), a_last, a_last.stride(0), self.dact[chain[-1]], dt,
                         rows, ly_prev.n_valid, ly_prev.n_block)
+            self._flush_group()
             for i in range(len(chain) - 1, -1, -1):
                 nm = chain[i]
                 a_in = self.act[chain[i - 1]] if i > 0 else self.zb
@@ -713,8 +820,14 @@ class Engine:
                     self._dgrad(nm, dy, dy.stride(0), a_in, a_in.stride(0), self.dact[chain[i - 1]], dt, rows, lp.n_valid,
                                 lp.n_block)
                 else:
-                    # dZ: fp32, no ReLU mask (Z is not an activation output); columns >= L zeroed
-                    self._dgrad(nm, dy, dy.stride(0), None, 0, self.dz, F32, rows, self.L, self.dz.shape[1])
+                    # dZ: fp32, no ReLU mask (Z is not an activation output).  With k-splits the partial sums reduce into
+                    # the cleared buffer and only columns [0, L) are meaningful (they are the only ones read)
+                    sk = self._head_split_k(rows) if self.layers[nm].out_pad >= 1024 else 1
+                    if not (sk > 1 and getattr(self, "_dz_cleared", False)):
+                        sk = 1
+                    self._dz_cleared = False
+                    self._dgrad(nm, dy, dy.stride(0), None, 0, self.dz, F32, rows, self.L, self.dz.shape[1], split_k=sk)
+                self._flush_group()
         # ---- reparameterisation backward (priors.py:86-89) ----
         if train_z:
             _abi.check(self.lib.dmvae_reparam_bwd(
@@ -737,6 +850,7 @@ class Engine:
             if train_c:
                 self._wgrad("ch", h[:, hp:], h.stride(0), self.dch, self.dch.stride(0), rows)
                 self._dgrad("ch", self.dch, self.dch.stride(0), h[:, hp:], h.stride(0), dh[:, hp:], dt, rows, hv, hp)
+            self._flush_group()                      # both heads' four GEMMs: one launch
             a_in = self.act[self.enc_chain[-1]]
             if train_z and train_c:
                 self._wgrad("ench", a_in, a_in.stride(0), dh, dh.stride(0), rows)
@@ -754,6 +868,7 @@ class Engine:
                     Wsub = self.W("ench", op=True)[:, c0:]
                     self._dgrad("ench", dh[:, c0:], dh.stride(0), a_in, a_in.stride(0), self.dact[self.enc_chain[-1]], dt,
                                 rows, lp.n_valid, lp.n_block, W=Wsub, ldw=self.layers["ench"].out_pad, n_out_pad=hp)
+            self._flush_group()
         else:
             if train_z:
                 a_in = self.act[self.enc_chain[-1]]
@@ -761,6 +876,7 @@ class Engine:
                 self._wgrad("zh", a_in, a_in.stride(0), self.dzh, self.dzh.stride(0), rows)
                 self._dgrad("zh", self.dzh, self.dzh.stride(0), a_in, a_in.stride(0), self.dact[self.enc_chain[-1]], dt,
                             rows, lp.n_valid, lp.n_block)
+                self._flush_group()
         # ---- encoder trunk ----
         if train_trunk:
             ec = self.enc_chain
@@ -773,6 +889,8 @@ class Engine:
                     lp = self.layers[ec[i - 1]]
                     self._dgrad(nm, dy, dy.stride(0), a_in, a_in.stride(0), self.dact[ec[i - 1]], dt, rows, lp.n_valid,
                                 lp.n_block)
+                self._flush_group()
+        self._end_group()
         self._join()
 
     # ------------------------------------------------------------------------------------------

@@ -51,7 +51,16 @@ def time_gemms(lib, ctx, rows=4096, iters=30, check=False, only="", dev=None, ve
         for kind in ("fwd", "dgrad", "wgrad"):
             e = _abi.GemmEpilogue()
             e.n_valid, e.n_block, e.pad_one, e.split_k = 1 << 30, 1 << 30, 0.0, 1
-            if kind == "fwd":
+            if kind == "fwd" and nout == 64 and os.environ.get("DMVAE_HEAD_SPLIT"):
+                # latent head as the engine runs it: fp32 output, k-splits reduced into a cleared buffer
+                Yf = torch.zeros(B, nout, dtype=torch.float32, device=dev)
+                e.out_dtype, e.act, e.split_k, e.accumulate = F32, _abi.ACT_NONE, int(os.environ["DMVAE_HEAD_SPLIT"]), 1
+                M, N, K = B, nout, kin
+                call = lambda: lib.dmvae_gemm(ctx, BF16, 0, 0, X.data_ptr(), kin, W.data_ptr(), nout, Yf.data_ptr(), nout,
+                                              M, N, K, C.byref(e), st())
+                ref = lambda: X.float() @ W.float()
+                out = Yf
+            elif kind == "fwd":
                 e.out_dtype, e.act = BF16, _abi.ACT_RELU
                 M, N, K = B, nout, kin
                 call = lambda: lib.dmvae_gemm(ctx, BF16, 0, 0, X.data_ptr(), kin, W.data_ptr(), nout, Y.data_ptr(), nout,
