@@ -291,7 +291,7 @@ def loss_and_grads(cfg, variables: Dict[str, np.ndarray], X, epsilon, kl_ratio=1
     out[loss_key].backward()
     grads = {k: (v.grad.detach().numpy().copy() if v.grad is not None else None) for k, v in V.items()}
     for k in keep:
-        grads["d_" + k] = out[k].grad.detach().numpy().copy()
+        grads["d_" + k] = None if out[k].grad is None else out[k].grad.detach().numpy().copy()
     outs = {k: v.detach().numpy().copy() for k, v in out.items()}
     return outs, grads
 

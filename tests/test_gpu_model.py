@@ -254,3 +254,41 @@ def test_chained_forward_is_bit_identical_to_layered():
             for a, b in zip(*outs):
                 assert torch.equal(a, b)
         eng.close()
+
+
+def test_pretrain_modes_match_oracle():
+    """define_pretrain_step (base_models.py:304-321): `vae_train_step` minimises recon_loss (epsilon = 0 in the
+    reference's feed, :340-342) over every variable, `prior_train_step` minimises latent_loss over the
+    encoder_network/c variables only.  Engine modes "vae" / "prior", fp32 tier, against autograd on the oracle."""
+    B = 96
+    cfg, eng, V = _make("dmvae", "fp32", B=B)
+    X, _, _ = _data(B, 784, 10, 10)
+    eps = np.zeros((B, 10), np.float32)
+    Xd, ed = torch.tensor(X, device="cuda"), torch.tensor(eps, device="cuda")
+    n = cfg.name
+    c_vars = [k for k in rg.trainable_names(cfg) if "/encoder_network/c/" in k]
+    assert len(c_vars) == 4
+    # ---- vae: gradient of recon_loss ----
+    out, g = rg.loss_and_grads(cfg, V, X, eps, loss_key="recon_loss")
+    eng.forward_backward(Xd, B, ed, mode="vae", kl_ratio=0.0)
+    torch.cuda.synchronize()
+    assert abs(float(eng.loss_out[0]) - out["recon_loss"]) <= 1e-4 * abs(out["recon_loss"])
+    for name in rg.trainable_names(cfg):
+        got = eng.get_variable(name, grad=True)
+        if g[name] is None or np.abs(g[name]).max() == 0:
+            assert np.abs(got).max() == 0, name            # c-head and prior tables: untouched by the reconstruction loss
+        else:
+            assert relerr(got, g[name]) < 1e-4, name
+    # ---- prior: gradient of latent_loss wrt the c-head only ----
+    eng.zero_grads()
+    out, g = rg.loss_and_grads(cfg, V, X, eps, loss_key="latent_loss")
+    eng.forward_backward(Xd, B, ed, mode="prior", kl_ratio=1.0, recon_scale=0.0)
+    torch.cuda.synchronize()
+    lo = eng.loss_out.cpu().numpy()
+    assert abs(lo[1] + lo[2] - out["latent_loss"]) <= 1e-4 * abs(out["latent_loss"])
+    for name in c_vars:
+        assert relerr(eng.get_variable(name, grad=True), g[name]) < 1e-4, name
+    for name in rg.trainable_names(cfg):
+        if name not in c_vars:
+            assert np.abs(eng.get_variable(name, grad=True)).max() == 0, name     # var_list restricts the update (:312-321)
+    eng.close()
