@@ -65,7 +65,8 @@ class ElboArgs(C.Structure):
                 ("d_mean_kl", c_void_p), ("d_log_var_kl", c_void_p), ("ld_dkl", c_int64),
                 ("d_logits", c_void_p), ("dlogits_dtype", c_int32), ("ld_dlogits", c_int64), ("dlogits_cols", c_int32),
                 ("d_Z_gamma", c_void_p), ("ld_dzg", c_int64),
-                ("w_scratch", c_void_p), ("f_scratch", c_void_p)]
+                ("w_scratch", c_void_p), ("f_scratch", c_void_p),
+                ("d_gate_extra", c_void_p), ("ld_dge", c_int64)]
 
 
 class MoeArgs(C.Structure):

@@ -209,6 +209,8 @@ __global__ void __launch_bounds__(kThreads) elbo_kernel(const ElboParams p) {
           C += q[jk] * (lq + logK);                                        // priors.py:195-199
           float gC = lq + q[jk] / (q[jk] + kEps0) + logK;
           G[jk] = r * (gC + 0.5f * A[jk]);
+          if (mode == DMVAE_MODE_VADE && a.d_gate_extra)       // another loss gated by gamma: same softmax Jacobian
+            G[jk] += __ldg(a.d_gate_extra + (int64_t)row * a.ld_dge + lane + 32 * jk) / s;
           Zk += 0.5f * q[jk] * A[jk];
           qG += q[jk] * G[jk];
         }

@@ -778,10 +778,13 @@ class Engine:
         ea.w_scratch, ea.f_scratch = self.w_scratch.data_ptr(), self.f_scratch.data_ptr()
         return ea
 
-    def elbo(self, X, xdt, rows, kl_ratio=1.0, inv_global_batch=None, recon_scale=1.0, prior_grads=True, klr_dev=None):
+    def elbo(self, X, xdt, rows, kl_ratio=1.0, inv_global_batch=None, recon_scale=1.0, prior_grads=True, klr_dev=None,
+             d_gate_extra=None):
         """Fused ELBO forward + backward and its cross-sample reductions."""
         s = (1.0 / rows) if inv_global_batch is None else inv_global_batch
         ea = self._elbo_args(X, xdt, rows, kl_ratio, s, recon_scale, klr_dev)
+        if d_gate_extra is not None:
+            ea.d_gate_extra, ea.ld_dge = d_gate_extra.data_ptr(), d_gate_extra.stride(0)
         self._join()
         t0 = self._tic("elbo")
         _abi.check(self.lib.dmvae_elbo_fwd_bwd(self.ctx, C.byref(ea), self._stream()))
@@ -1010,12 +1013,20 @@ class Engine:
         if not train:
             return
         if self.model == "vade":
-            raise NotImplementedError("training the VaDE-gated MoE (gradient of the supervised loss through gamma) is not "
-                                      "implemented yet; dmoe / dvmoe are")
-        # gate gradient through the softmax into the c-head logits (added to the ELBO's own d_logits when lossVAE)
-        _abi.check(self.lib.dmvae_softmax_bwd_add(self.ctx, rows, self.K, self.qc.data_ptr(), self.moe_dgate.data_ptr(), E,
-                                                  self.dch.data_ptr(), self.dt, self.dch.stride(0), 1 if lossVAE else 0,
-                                                  self.dch.shape[1], st()))
+            # the gate is gamma = get_cluster_probs(Z) (models.py:74, priors.py:91-102): the supervised loss reaches Z, mean,
+            # log_var and the prior tables through it.  Second pass of the fused ELBO kernel with d loss / d gamma added
+            # through gamma's softmax Jacobian (the first pass produced gamma for the experts' mixture).
+            self._join()
+            self.elbo(Xs, xdt, rows, kl_ratio if lossVAE else 0.0, None, 1.0 if lossVAE else 0.0, prior_grads=True,
+                      d_gate_extra=self.moe_dgate)
+            self._join()
+            if not lossVAE:                      # no decoder backward: dZ has the gamma path only
+                _abi.check(self.lib.dmvae_zero_f32(self.ctx, self.dz.data_ptr(), rows * self.dz.stride(0), st()))
+        else:
+            # gate gradient through the softmax into the c-head logits (added to the ELBO's own d_logits when lossVAE)
+            _abi.check(self.lib.dmvae_softmax_bwd_add(self.ctx, rows, self.K, self.qc.data_ptr(), self.moe_dgate.data_ptr(), E,
+                                                      self.dch.data_ptr(), self.dt, self.dch.stride(0), 1 if lossVAE else 0,
+                                                      self.dch.shape[1], st()))
         self._wgrad("moe", a_in, a_in.stride(0), self.moe_dpred, self.moe_dpred.stride(0), rows)
         dme = None
         if feat:

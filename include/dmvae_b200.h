@@ -188,6 +188,10 @@ typedef struct dmvae_elbo_args {
   float* d_Z_gamma; int64_t ld_dzg;                            /* fp32 [rows,L] gradient reaching Z through gamma (VADE) */
   float* w_scratch;        /* fp32 [rows,K]: d_s (VADE) */
   float* f_scratch;        /* fp32 [rows,2L]: [g_mbar | g_pbar] (SAMPLED) */
+  /* VADE only, optional: d(other loss)/d gamma [rows,K] (already scaled by that loss's 1/batch), e.g. the MoE's
+   * supervised loss gated by gamma (models.py:74).  Added through gamma's softmax Jacobian to d_s, so it reaches Z,
+   * mean / log_var and the prior tables together with the ELBO's own gradient. */
+  const float* d_gate_extra; int64_t ld_dge;
 } dmvae_elbo_args;
 int dmvae_elbo_fwd_bwd(dmvae_ctx* ctx, const dmvae_elbo_args* a, void* stream);
 

@@ -105,19 +105,26 @@ def _moe_oracle(cfg, V, X, Y, eps, scope, classification, lossVAE, featLearn, ge
     return float(mo["recon_loss"]), float(mo["error"]), float(out["loss"]), grads
 
 
-@pytest.mark.parametrize("kind,tier", [("dmoe", "fp32"), ("dvmoe", "fp32"), ("dmoe", "bf16"), ("dvmoe", "bf16")])
+@pytest.mark.parametrize("kind,tier", [("dmoe", "fp32"), ("dvmoe", "fp32"), ("vademoe", "fp32"), ("dmoe", "bf16"),
+                                       ("dvmoe", "bf16"), ("vademoe", "bf16")])
 def test_moe_step_matches_oracle(kind, tier):
-    """DeepMoE (lossVAE=0, featLearn=0, latent 1; runLR_MOE.sh) and DeepVariationalMoE (lossVAE=1, featLearn=1;
-    runOur.sh): supervised loss, error count, and every parameter gradient of one step, 16 classification experts."""
+    """DeepMoE (lossVAE=0, featLearn=0, latent 1; runLR_MOE.sh), DeepVariationalMoE (lossVAE=1, featLearn=1; runOur.sh)
+    and VaDEMoE (gate = gamma(Z), models.py:265-275): supervised loss, error count, and every parameter gradient of one
+    step, 16 classification experts."""
     from dmvae_b200.engine import Engine
     B, D, E, O = 128, 784, 16, 10
     lossVAE, feat = (0, 0) if kind == "dmoe" else (1, 1)
     L = 1 if kind == "dmoe" else 10
     scope = "/".join([kind] * 3)
-    cfg = rg.GraphConfig(name=kind, input_dim=D, latent_dim=L, n_classes=E)
     moe = dict(n_experts=E, output_dim=O, featLearn=bool(feat), lossVAE=bool(lossVAE), classification=True, scope=scope)
-    eng = Engine(model="dmvae", input_type="binary", input_dim=D, latent_dim=L, n_classes=E, trunk=(500, 500), head=2000,
-                 decoder=(2000, 500, 500), name=kind, gemm_dtype=tier, max_rows=B, moe=moe)
+    if kind == "vademoe":
+        cfg = rg.GraphConfig.vade(name=kind, input_dim=D, latent_dim=L, n_classes=E)
+        eng = Engine(model="vade", input_type="binary", input_dim=D, latent_dim=L, n_classes=E, trunk=(2000, 500, 500), head=0,
+                     decoder=(500, 500, 2000), name=kind, gemm_dtype=tier, max_rows=B, moe=moe)
+    else:
+        cfg = rg.GraphConfig(name=kind, input_dim=D, latent_dim=L, n_classes=E)
+        eng = Engine(model="dmvae", input_type="binary", input_dim=D, latent_dim=L, n_classes=E, trunk=(500, 500), head=2000,
+                     decoder=(2000, 500, 500), name=kind, gemm_dtype=tier, max_rows=B, moe=moe)
     V = rg.init_variables(cfg, 0)
     rs = np.random.RandomState(11)
     I = L if feat else D

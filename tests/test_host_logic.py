@@ -32,14 +32,14 @@ def test_abi_structs_match_c_layout():
     import subprocess
     import tempfile
     from dmvae_b200 import _abi
-    src = '#include <stdio.h>\n#include "dmvae_b200.h"\nint main(){printf("%zu %zu %zu %zu\\n", sizeof(dmvae_gemm_epilogue), ' \
-          'sizeof(dmvae_reparam_args), sizeof(dmvae_elbo_args), sizeof(dmvae_moe_args));return 0;}\n'
+    src = '#include <stdio.h>\n#include "dmvae_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu\\n", sizeof(dmvae_gemm_epilogue), ' \
+          'sizeof(dmvae_reparam_args), sizeof(dmvae_elbo_args), sizeof(dmvae_moe_args), sizeof(dmvae_chain_gemm));return 0;}\n'
     with tempfile.TemporaryDirectory() as d:
         open(os.path.join(d, "p.c"), "w").write(src)
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), os.path.join(d, "p.c"), "-o", os.path.join(d, "p")])
         sizes = [int(x) for x in subprocess.check_output([os.path.join(d, "p")]).split()]
     assert sizes == [ctypes.sizeof(_abi.GemmEpilogue), ctypes.sizeof(_abi.ReparamArgs), ctypes.sizeof(_abi.ElboArgs),
-                     ctypes.sizeof(_abi.MoeArgs)]
+                     ctypes.sizeof(_abi.MoeArgs), ctypes.sizeof(_abi.ChainGemm)]
 
 
 def test_no_cpu_fallback_without_cuda():
