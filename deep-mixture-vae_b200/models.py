@@ -205,7 +205,7 @@ class DeepVariationalMoE(MoE):
 
 
 class VaDEMoE(MoE):
-    """models.py:265-275 (forward / evaluation; see Engine.moe_step for the training status)."""
+    """models.py:265-275: the gate is gamma = get_cluster_probs(Z); training sends the supervised gradient through it."""
 
     def __init__(self, name, input_type, input_dim, latent_dim, output_dim, n_experts, classification, activation=None,
                  initializer=None, featLearn=1, cnn=1):
