@@ -17,6 +17,7 @@ The host-side arithmetic (shard ranges, bucket layout) is device-agnostic and co
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import List, Optional, Tuple
 
 import torch
@@ -102,7 +103,6 @@ class DataParallel:
         dist.broadcast(engine.params, src=0, group=group)
         engine.sync_operand_copy()
         torch.cuda.synchronize(engine.device)
-        self.shard = shard_range(engine.n_params, self.rank, self.world)
         self._opt_shards = {}
 
     # ---- symmetric memory -------------------------------------------------------------------------------
@@ -137,31 +137,77 @@ class DataParallel:
         self._b_ptrs = VP(*[(p + 8 * P) if eng.params_op is not None else 0 for p in ptrs])
         self._master_stale = False
 
-    def _opt_shard_state(self, opt):
-        """Adam slots of the owned shard only (the other ranks own the rest)."""
-        key = id(opt)
+    # ---- ranges: the flat buffer is exchanged as encoder | decoder | tail (experts, prior tables).  The decoder's
+    #      gradients are complete half way through the backward pass, so their exchange overlaps the encoder's
+    #      backward GEMMs on a forked stream; the rest is exchanged at the end of the step. ----
+    def ranges(self):
+        eng = self.eng
+        if not self.overlap_decoder:
+            return [(0, eng.n_params)]
+        dec0 = eng.layers[eng.dec_chain[0]].offset
+        dx = eng.layers["decx"]
+        dec1 = dx.offset + dx.size
+        return [(0, dec0), (dec0, dec1), (dec1, eng.n_params)]
+
+    def range_shard(self, ridx, rank=None):
+        lo, hi = self.ranges()[ridx]
+        b, e = shard_range(hi - lo, self.rank if rank is None else rank, self.world)
+        return lo + b, lo + e
+
+    def _opt_shard_state(self, opt, ridx):
+        """Adam slots of the owned shard of one range (the other ranks own the rest)."""
+        key = (id(opt), ridx)
         if key not in self._opt_shards:
-            b, e = self.shard
+            b, e = self.range_shard(ridx)
             n = max(e - b, 4)
             self._opt_shards[key] = (torch.zeros(n, dtype=torch.float32, device=self.eng.device),
                                      torch.zeros(n, dtype=torch.float32, device=self.eng.device))
         return self._opt_shards[key]
 
-    # ---- the exchange + update ---------------------------------------------------------------------------
-    def update(self, opt, use_dev: bool = False):
+    def _exchange(self, opt, lr_t, lr_dev, ridxs, ch):
         eng, abi = self.eng, self._abi
-        lr_t = 0.0 if use_dev else opt.next_lr_t()
-        lr_dev = (opt.state_dev.data_ptr() + 12) if use_dev else None
-        if self.mode == "p2p":
-            m, v = self._opt_shard_state(opt)
-            b, e = self.shard
-            self.hdl.barrier(channel=0)                   # every rank's gradients are complete
+        self.hdl.barrier(channel=ch)                      # every rank's gradients of these ranges are complete
+        for ridx in ridxs:
+            b, e = self.range_shard(ridx)
+            if e <= b:
+                continue
+            m, v = self._opt_shard_state(opt, ridx)
             abi.check(eng.lib.dmvae_dp_reduce_adam(eng.ctx, self.rank, self.world, self._g_ptrs, self._p_ptrs,
                                                    self._b_ptrs, m.data_ptr(), v.data_ptr(), eng.n_params, b, e, lr_t,
                                                    lr_dev, opt.beta1, opt.beta2, opt.eps, 0, eng._stream()))
-            self.hdl.barrier(channel=1)                   # every replica updated, every gradient shard consumed
-            # clear the local gradient buffer (split-K accumulates into it): local HBM instead of 7/8 remote stores
-            abi.check(eng.lib.dmvae_zero_f32(eng.ctx, eng.grads.data_ptr(), eng.n_params, eng._stream()))
+        self.hdl.barrier(channel=ch + 1)                  # every replica updated, every gradient shard consumed
+        # clear the local gradients of these ranges (split-K accumulates into them): local HBM, not 7/8 remote stores
+        for ridx in ridxs:
+            lo, hi = self.ranges()[ridx]
+            if hi > lo:
+                abi.check(eng.lib.dmvae_zero_f32(eng.ctx, eng.grads.data_ptr() + 4 * lo, hi - lo, eng._stream()))
+
+    # Measured on 2 x B200: the extra barrier pair and launches of the early exchange cost more than the overlap hides
+    # (0.3645 vs 0.3558 ms / step), so one exchange at the end of the step is the default; DMVAE_DP_OVERLAP=1 enables it.
+    overlap_decoder = os.environ.get("DMVAE_DP_OVERLAP", "0") == "1"
+
+    def early(self, opt, use_dev: bool):
+        """Exchange + Adam of the decoder range; called (on a forked stream) as soon as the decoder's weight gradients are
+        queued.  update() then handles the other ranges."""
+        if self.mode != "p2p" or not self.overlap_decoder:
+            return
+        self._lr_t_step = 0.0 if use_dev else opt.next_lr_t()
+        lr_dev = (opt.state_dev.data_ptr() + 12) if use_dev else None
+        self._exchange(opt, self._lr_t_step, lr_dev, [1], 2)
+        self._early_done = True
+
+    # ---- the exchange + update ---------------------------------------------------------------------------
+    def update(self, opt, use_dev: bool = False):
+        eng, abi = self.eng, self._abi
+        early = getattr(self, "_early_done", False)
+        self._early_done = False
+        if early:
+            lr_t = self._lr_t_step
+        else:
+            lr_t = 0.0 if use_dev else opt.next_lr_t()
+        lr_dev = (opt.state_dev.data_ptr() + 12) if use_dev else None
+        if self.mode == "p2p":
+            self._exchange(opt, lr_t, lr_dev, [0, 2] if early else list(range(len(self.ranges()))), 0)
             self._master_stale = self.master_sharded
         else:
             dist.all_reduce(eng.grads, op=dist.ReduceOp.SUM, group=self.group)
@@ -186,10 +232,11 @@ class DataParallel:
         for r in range(self.world):
             if r == self.rank:
                 continue
-            b, e = shard_range(n, r, self.world)
-            if e > b:
-                peer = self.hdl.get_buffer(r, (n,), torch.float32, 0)
-                eng.params[b:e].copy_(peer[b:e])
+            peer = self.hdl.get_buffer(r, (n,), torch.float32, 0)
+            for ridx in range(len(self.ranges())):
+                b, e = self.range_shard(ridx, r)
+                if e > b:
+                    eng.params[b:e].copy_(peer[b:e])
         torch.cuda.current_stream(eng.device).synchronize()
         self._master_stale = False
 

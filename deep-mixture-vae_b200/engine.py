@@ -831,6 +831,10 @@ class Engine:
                     self._dz_cleared = False
                     self._dgrad(nm, dy, dy.stride(0), None, 0, self.dz, F32, rows, self.L, self.dz.shape[1], split_k=sk)
                 self._flush_group()
+        # data parallel: the decoder's gradients are complete - exchange them while the encoder's backward runs
+        dpo = getattr(self, "_dp_opt", None)
+        if self.dp is not None and dpo is not None and through_decoder and train_decoder and self.timers is None:
+            self._fork(lambda: self.dp.early(dpo[0], dpo[1]))
         # ---- reparameterisation backward (priors.py:86-89) ----
         if train_z:
             _abi.check(self.lib.dmvae_reparam_bwd(
@@ -1053,7 +1057,9 @@ class Engine:
         if use_graph and eps is None and gumbel is None:
             return self._train_step_graph(X, rows, opt, kl_ratio, mode, recon_scale)
         inv, off = self._dp_scale(rows)
+        self._dp_opt = (opt, False) if mode == "all" else None
         self.forward_backward(X, rows, eps, gumbel, kl_ratio, inv, off, recon_scale, True, mode)
+        self._dp_opt = None
         self._update(opt)
         self.step_count += 1
         if self.dp is not None:
@@ -1079,7 +1085,9 @@ class Engine:
             # first use of this signature: one eager step (also warms the TMA-descriptor cache and the kernels'
             # shared-memory attributes), then capture the same sequence for every later step
             inv, off = self._dp_scale(rows)
+            self._dp_opt = (opt, False) if mode == "all" else None
             self.forward_backward(X, rows, None, None, kl_ratio, inv, off, recon_scale, True, mode)
+            self._dp_opt = None
             self._update(opt)
             self.step_count += 1
             torch.cuda.current_stream(self.device).synchronize()
@@ -1088,7 +1096,9 @@ class Engine:
             with torch.cuda.graph(g):
                 _abi.check(self.lib.dmvae_step_tick(self.ctx, opt.state_dev.data_ptr(), opt.lr, opt.beta1, opt.beta2,
                                                     self._stream()))
+                self._dp_opt = (opt, True) if mode == "all" else None
                 self.forward_backward(X, rows, None, None, kl_ratio, inv, off, recon_scale, True, mode, dev_state=opt)
+                self._dp_opt = None
                 self._update(opt, use_dev=True)
             n_nodes = int(self.lib.dmvae_ctx_launch_count(self.ctx)) - l0
             self._graphs[key] = (g, n_nodes)
