@@ -209,12 +209,10 @@ gemm_chain_kernel(const __grid_constant__ ChainParams P) {
       decode_unit(P, u, e, un);
       const ChainLayer& Ly = P.L[e];
       const uint32_t as = ui & 1u, aph = (ui >> 1) & 1u;
-      mbar_wait(tfull_bar(as), aph);
-      tcgen05_fence_after();
       const int bnh = Ly.bn >> 1;
       epilogue_warp(tmem_base + as * CH_BN + ((uint32_t)(q * 32) << 16), half * bnh, (half + 1) * bnh,
                     un.m_blk * 2 * BM + (int)rank * BM + q * 32, un.n_blk * Ly.bn, Ly.M, Ly.N, &Ly.tmC, Ly.ep, un.kb0 == 0,
-                    my_stage, lane, lead_tempty0 + as * 8, (Ly.fuse && half == 0) ? &P.ra : nullptr);
+                    my_stage, lane, lead_tempty0 + as * 8, (Ly.fuse && half == 0) ? &P.ra : nullptr, tfull_bar(as), aph);
       if (Ly.publish) {
         // publish: this warp's part of the tile is in global memory
         if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");

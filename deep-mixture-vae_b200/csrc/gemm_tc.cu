@@ -122,12 +122,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else {
     // ===================== epilogue =====================
-    mbar_wait(tmem_full_bar, 0);
-    tcgen05_fence_after();
     const int q = warp & 3;                  // TMEM lane quarter this warp may access
-    if (nkb > 0)
+    if (nkb > 0) {
       epilogue_warp(tmem_base + ((uint32_t)(q * 32) << 16), 0, BN, m0 + q * 32, n0, M, N, &tmC, ep, blockIdx.z == 0,
-                    epi_stage + q * kEpiStageBytes, lane, 0u);
+                    epi_stage + q * kEpiStageBytes, lane, 0u, nullptr, tmem_full_bar, 0u);
+    } else {
+      mbar_wait(tmem_full_bar, 0);
+      tcgen05_fence_after();
+    }
   }
   // ===================== teardown =====================
   tcgen05_fence_before();
@@ -286,11 +288,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       int m_blk, n_blk, kb0, kb1;
       decode(u, m_blk, n_blk, kb0, kb1);
       const uint32_t as = ui & 1u, aph = (ui >> 1) & 1u;
-      mbar_wait(tfull_bar(as), aph);
-      tcgen05_fence_after();
       epilogue_warp(tmem_base + as * BN + ((uint32_t)(q * 32) << 16), half * (BN / 2), (half + 1) * (BN / 2),
                     m_blk * 2 * BM + (int)rank * BM + q * 32, n_blk * BN, M, N, &tmC, ep, kb0 == 0, my_stage, lane,
-                    lead_tempty0 + as * 8);
+                    lead_tempty0 + as * 8, nullptr, tfull_bar(as), aph);
     }
   }
   // ===================== teardown =====================

@@ -223,7 +223,8 @@ template <bool OUT_BF16, bool RELU, bool MASK, bool FUSE = false>
 __device__ __forceinline__ void epilogue_warp_cols(uint32_t taddr, int col_begin, int col_end, int m_base, int n0, int M, int N,
                                                    const CUtensorMap* tmC, const EpiParams& ep, bool first_split,
                                                    uint32_t stage, int lane, uint32_t arrive_bar,
-                                                   const dmvae_reparam_args* fuse = nullptr) {
+                                                   const dmvae_reparam_args* fuse = nullptr, uint32_t wait_bar = 0,
+                                                   uint32_t wait_parity = 0) {
   constexpr int CP = OUT_BF16 ? 64 : 32;                  // columns per 128-byte slab row
   const bool padded = ep.n_valid < ep.n_block;
   const uint32_t st_row = stage + lane * 128;
@@ -232,6 +233,21 @@ __device__ __forceinline__ void epilogue_warp_cols(uint32_t taddr, int col_begin
   const bool m_ok = m < M;
   if (col_end > N - n0) col_end = N - n0;                 // N % 8 == 0
   bool arrived = false;
+  // ReLU-mask rows (dgrad): 64 bytes per thread and 32 columns, software-pipelined one chunk ahead; the first chunk is
+  // requested BEFORE waiting for the accumulator, so its DRAM / L2 latency hides behind the main loop
+  auto load_mask = [&](int n, uint4 (&mk)[4]) {
+#pragma unroll
+    for (int g4 = 0; g4 < 4; ++g4) {
+      mk[g4] = make_uint4(0u, 0u, 0u, 0u);
+      if (m_ok && n + g4 * 8 < N) mk[g4] = __ldg(reinterpret_cast<const uint4*>(mrow + n) + g4);
+    }
+  };
+  uint4 mk_next[4];
+  if (MASK && col_begin < col_end) load_mask(n0 + col_begin, mk_next);
+  if (wait_bar != 0) {
+    mbar_wait(wait_bar, wait_parity);
+    tcgen05_fence_after();
+  }
 #pragma unroll 1
   for (int c0 = col_begin; c0 < col_end; c0 += CP) {
     // the TMA store of the previous slab must have finished READING shared memory before it is overwritten
@@ -245,10 +261,8 @@ __device__ __forceinline__ void epilogue_warp_cols(uint32_t taddr, int col_begin
       uint4 mk[4];
       if (MASK) {
 #pragma unroll
-        for (int g4 = 0; g4 < 4; ++g4) {
-          mk[g4] = make_uint4(0u, 0u, 0u, 0u);
-          if (m_ok && n + g4 * 8 < N) mk[g4] = __ldg(reinterpret_cast<const uint4*>(mrow + n) + g4);
-        }
+        for (int g4 = 0; g4 < 4; ++g4) mk[g4] = mk_next[g4];
+        if (c0 + sub + 32 < col_end) load_mask(n + 32, mk_next);
       }
       uint32_t raw[32];
       tmem_ld32(taddr + (uint32_t)(c0 + sub), raw);
@@ -343,9 +357,10 @@ __device__ __forceinline__ void epilogue_warp_cols(uint32_t taddr, int col_begin
 // warp-uniform dispatch to the specialised epilogues
 __device__ __forceinline__ void epilogue_warp(uint32_t taddr, int col_begin, int col_end, int m_base, int n0, int M, int N,
                                               const CUtensorMap* tmC, const EpiParams& ep, bool first_split, uint32_t stage,
-                                              int lane, uint32_t arrive_bar, const dmvae_reparam_args* fuse = nullptr) {
+                                              int lane, uint32_t arrive_bar, const dmvae_reparam_args* fuse = nullptr,
+                                              uint32_t wait_bar = 0, uint32_t wait_parity = 0) {
   const bool relu = ep.act == DMVAE_ACT_RELU, mask = ep.mask != nullptr;
-#define EPI_GO(B, R, K) epilogue_warp_cols<B, R, K>(taddr, col_begin, col_end, m_base, n0, M, N, tmC, ep, first_split, stage, lane, arrive_bar)
+#define EPI_GO(B, R, K) epilogue_warp_cols<B, R, K>(taddr, col_begin, col_end, m_base, n0, M, N, tmC, ep, first_split, stage, lane, arrive_bar, nullptr, wait_bar, wait_parity)
   if (ep.out_dtype == DMVAE_BF16) {
     if (mask) EPI_GO(true, false, true);                  // dgrad (activation already applied upstream)
     else if (relu) EPI_GO(true, true, false);             // forward hidden layer
@@ -355,7 +370,7 @@ __device__ __forceinline__ void epilogue_warp(uint32_t taddr, int col_begin, int
     else if (relu) EPI_GO(false, true, false);
     else if (fuse)
       epilogue_warp_cols<false, false, false, true>(taddr, col_begin, col_end, m_base, n0, M, N, tmC, ep, first_split, stage, lane,
-                                                    arrive_bar, fuse);   // latent head with the reparameterisation fused
+                                                    arrive_bar, fuse, wait_bar, wait_parity);   // latent head + fused reparameterisation
     else EPI_GO(false, false, false);                     // heads, dZ, weight gradients
   }
 #undef EPI_GO

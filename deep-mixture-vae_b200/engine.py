@@ -833,7 +833,8 @@ class Engine:
                 self._flush_group()
         # data parallel: the decoder's gradients are complete - exchange them while the encoder's backward runs
         dpo = getattr(self, "_dp_opt", None)
-        if self.dp is not None and dpo is not None and through_decoder and train_decoder and self.timers is None:
+        if (self.dp is not None and dpo is not None and getattr(self.dp, "overlap_decoder", False) and through_decoder
+                and train_decoder and self.timers is None):
             self._fork(lambda: self.dp.early(dpo[0], dpo[1]))
         # ---- reparameterisation backward (priors.py:86-89) ----
         if train_z:

@@ -28,6 +28,33 @@ def test_shard_ranges_cover_and_align():
     assert global_row_offset(3, 4096) == 12288
 
 
+def test_range_shards_partition_the_flat_buffer():
+    """DataParallel.range_shard: with or without the early decoder exchange, the ranks' shards of all ranges tile the
+    flat parameter buffer exactly once and stay float4-aligned (host logic only: a stub engine with the real Layout)."""
+    from dmvae_b200 import dp
+    from dmvae_b200.engine import Layout
+
+    class Stub:
+        pass
+    lay = Layout(model="dmvae", input_dim=784, latent_dim=10, n_classes=10, trunk=(500, 500), head=2000,
+                 decoder=(2000, 500, 500), name="dmvae")
+    for overlap in (False, True):
+        for world in (1, 2, 4, 8):
+            covered = np.zeros(lay.n_params, np.int32)
+            for rank in range(world):
+                d = dp.DataParallel.__new__(dp.DataParallel)
+                eng = Stub()
+                eng.layers, eng.dec_chain, eng.n_params = lay.layers, lay.dec_chain, lay.n_params
+                d.eng, d.rank, d.world, d.overlap_decoder = eng, rank, world, overlap
+                rr = d.ranges()
+                assert rr[0][0] == 0 and rr[-1][1] == lay.n_params and len(rr) == (3 if overlap else 1)
+                for i in range(len(rr)):
+                    b, e = d.range_shard(i)
+                    assert b % 4 == 0 and e % 4 == 0 and rr[i][0] <= b <= e <= rr[i][1]
+                    covered[b:e] += 1
+            assert (covered == 1).all()
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
