@@ -648,6 +648,7 @@ class Engine:
 
     def reparam(self, rows: int, eps_injected: bool, gumbel_injected: bool, row_offset: int = 0, step: Optional[int] = None,
                 step_dev: Optional[int] = None):
+        self._join()                 # the step-tick / output-clearing work forked at the start of the step
         ra = _abi.ReparamArgs()
         ra.step_dev = step_dev
         ra.rows, ra.L, ra.K = rows, self.L, self.K
@@ -716,6 +717,7 @@ class Engine:
     def forward_chain(self, rows: int, eps_injected: bool, row_offset: int = 0, step: Optional[int] = None,
                       step_dev: Optional[int] = None):
         """encode + reparam + decode (base_models.py:218-293) as one dmvae_gemm_chain launch."""
+        self._join()                 # the step-tick forked at the start of the step (the fused epilogue reads the step)
         relu, none = _abi.ACT_RELU, _abi.ACT_NONE
         ent, idx = [], {}
         a, prev = self.act["x"], -1
@@ -1095,8 +1097,10 @@ class Engine:
             g = torch.cuda.CUDAGraph()
             l0 = int(self.lib.dmvae_ctx_launch_count(self.ctx))
             with torch.cuda.graph(g):
-                _abi.check(self.lib.dmvae_step_tick(self.ctx, opt.state_dev.data_ptr(), opt.lr, opt.beta1, opt.beta2,
-                                                    self._stream()))
+                # the per-step scalars (Philox step, Adam lr_t) are first read by the reparameterisation: advance them on
+                # the side stream, off the head of the critical path
+                self._fork(lambda: _abi.check(self.lib.dmvae_step_tick(self.ctx, opt.state_dev.data_ptr(), opt.lr,
+                                                                        opt.beta1, opt.beta2, self._stream())))
                 self._dp_opt = (opt, True) if mode == "all" else None
                 self.forward_backward(X, rows, None, None, kl_ratio, inv, off, recon_scale, True, mode, dev_state=opt)
                 self._dp_opt = None
