@@ -442,18 +442,14 @@ constexpr int kFastThreads = 32 * (8 + kLatWarps);
 
 // shared-memory plan of the row-tile kernel (floats)
 struct RowTileSmem {
-  int tab_m, tab_iv, sum_plv, mu, lv, q, g, dmu, dlv, R, total;
-  __host__ __device__ RowTileSmem(int L, int K, int Ls, int Ks) {
+  int tab, sum_plv, ml, q, g, R, total;
+  __host__ __device__ RowTileSmem(int L, int K) {
     int o = 0;
-    tab_m = o; o += K * Ls;
-    tab_iv = o; o += K * Ls;
+    tab = o; o += 2 * K * L;                // float2 (prior mean, exp(-prior log-variance)) [K][L]
     sum_plv = o; o += (K + 3) & ~3;
-    mu = o; o += kFastRows * Ls;
-    lv = o; o += kFastRows * Ls;            // log_var, then exp(log_var)
-    q = o; o += kFastRows * Ks;             // logits -> q(c|x)
-    g = o; o += kFastRows * Ks;             // G_k -> d_logits
-    dmu = o; o += kFastRows * Ls;
-    dlv = o; o += kFastRows * Ls;
+    ml = o; o += 2 * kFastRows * L;         // float2 (mean, exp(log_var)) [rows][L]
+    q = o; o += (kFastRows * K + 3) & ~3;   // logits -> q(c|x), [rows][K]
+    g = o; o += (kFastRows * K + 3) & ~3;   // G_k -> d_logits
     R = o; o += kFastRows;
     total = o;
   }
@@ -486,77 +482,87 @@ __device__ __forceinline__ float recon1_rt(float x, float d, float s, float& g) 
   }
 }
 
-__device__ __forceinline__ uint32_t h2_bits(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
-__device__ __forceinline__ __half2 bits_h2(uint32_t u) { return *reinterpret_cast<__half2*>(&u); }
-
-// 8 targets of a shared-memory tile as 4 half2 pairs
-template <typename T>
-__device__ __forceinline__ void tile8_half2(uint32_t a, __half2 (&xh)[4]) {
-  float v[8];
-  Tile8<T>::load(a, v);
+// 8 targets of a shared-memory tile as floats, optionally centred (x - 0.5)
+template <typename T, bool CENTRED>
+__device__ __forceinline__ void tile8_x(uint32_t a, float (&x)[8]) {
+  Tile8<T>::load(a, x);
+  if (CENTRED) {
 #pragma unroll
-  for (int i = 0; i < 4; ++i) xh[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+    for (int i = 0; i < 8; ++i) x[i] -= 0.5f;
+  }
 }
 template <>
-__device__ __forceinline__ void tile8_half2<uint8_t>(uint32_t a, __half2 (&xh)[4]) {
+__device__ __forceinline__ void tile8_x<uint8_t, true>(uint32_t a, float (&x)[8]) {
   uint32_t lo, hi;
   asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(lo), "=r"(hi) : "r"(a));
-  // bytes (b0, b1) -> halves 0x64b0, 0x64b1 = 1024 + b exactly; minus 1024: one PRMT + one HADD2 per pair
-  const __half2 k1024 = __float2half2_rn(1024.f);
-  xh[0] = __hsub2(bits_h2(__byte_perm(lo, 0x64646464u, 0x4140)), k1024);
-  xh[1] = __hsub2(bits_h2(__byte_perm(lo, 0x64646464u, 0x4342)), k1024);
-  xh[2] = __hsub2(bits_h2(__byte_perm(hi, 0x64646464u, 0x4140)), k1024);
-  xh[3] = __hsub2(bits_h2(__byte_perm(hi, 0x64646464u, 0x4342)), k1024);
-}
-
-// bf16 tier (bf16 decoder logits in, bf16 gradient out; tolerance 2e-2): packed half2 arithmetic, two elements per
-// issue slot.  e^{-|d|} and tanh are one f16x2 MUFU per pair; log1p(t) = t P4(t).  Simulated against fp64 on
-// N(0,3) logits: per-sample sum within 6e-5 relative, gradient within 4e-4 absolute (below its bf16 rounding).
-// The loss terms are accumulated and the gradient is scaled in fp32 (s = 1/batch underflows fp16).
-template <int INPUT>
-__device__ __forceinline__ float recon8_h2(const __half2 (&xh)[4], const uint32_t (&dw)[4], uint32_t (&gw)[4], float s) {
-  float acc = 0.f;
-  const __half2 zero = __float2half2_rn(0.f), half = __float2half2_rn(0.5f);
+  // byte b -> float bits 0x4700bb00 = 2^15 + b (ulp 2^-8), minus (2^15 + 0.5): b - 0.5 exactly; one PRMT + one FADD
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const __half2 d = __floats2half2_rn(__uint_as_float(dw[i] << 16), __uint_as_float(dw[i] & 0xffff0000u));
-    __half2 loss, gd;
-    if (INPUT == DMVAE_INPUT_BINARY) {
-      uint32_t tw, thw;
-      asm("ex2.approx.f16x2 %0, %1;" : "=r"(tw) : "r"(h2_bits(__hmul2(__habs2(d), __float2half2_rn(-1.4426950408889634f)))));
-      const __half2 t = bits_h2(tw);
-      __half2 pl = __float2half2_rn(0.041551114473448364f);
-      pl = __hfma2(pl, t, __float2half2_rn(-0.15783837660869268f));
-      pl = __hfma2(pl, t, __float2half2_rn(0.30656109993887143f));
-      pl = __hfma2(pl, t, __float2half2_rn(-0.4970308426636867f));
-      pl = __hfma2(pl, t, __float2half2_rn(0.9999449934273393f));
-      loss = __hfma2(pl, t, __hfma2(__hneg2(d), xh[i], __hmax2(d, zero)));
-      asm("tanh.approx.f16x2 %0, %1;" : "=r"(thw) : "r"(h2_bits(__hmul2(d, half))));
-      gd = __hsub2(__hfma2(bits_h2(thw), half, half), xh[i]);   // sigmoid(d) - x
-    } else {
-      gd = __hsub2(d, xh[i]);
-      loss = __hmul2(__hmul2(gd, half), gd);
-    }
-    const float2 lf = __half22float2(loss), gf = __half22float2(gd);
-    acc += lf.x;
-    acc += lf.y;
-    __nv_bfloat162 gb = __floats2bfloat162_rn(gf.x * s, gf.y * s);
-    gw[i] = *reinterpret_cast<uint32_t*>(&gb);
+    x[i] = __uint_as_float(__byte_perm(lo, 0x47000000u, 0x7504 | (i << 4))) - 32768.5f;
+    x[4 + i] = __uint_as_float(__byte_perm(hi, 0x47000000u, 0x7504 | (i << 4))) - 32768.5f;
   }
-  return acc;
 }
 
-template <typename TX, typename TD, int INPUT>
-__global__ void __launch_bounds__(kFastThreads, 3) elbo_rowtile_kernel(const ElboParams p) {
+// bf16 tier (bf16 decoder logits in, bf16 gradient out; tolerance 2e-2), 8 elements of one row.  Binary likelihood,
+// with h = |d|/2, u = tanh(h) (ONE MUFU per element), xc = x - 1/2:
+//   sigmoid(d) - x            = sign(d) u / 2 - xc
+//   max(d,0) - d x            = h - d xc
+//   log1p(e^{-|d|})           = ln 2 - ln(1 + u)          ->  sum_d = n ln 2 - ln prod_d (1 + u_d)
+// so the log term costs one FFMA per element (a running product, <= 2^n) and one lg2 per lane and row.
+// PRECISE keeps e^{-|d|} from a second MUFU (ex2, 2^-22) for the product instead of tanh's 2^-11.
+// Everything is fp32: ~11 issue slots per element against ~19 for the earlier packed-half2 formulation (whose f16x2 MUFUs
+// split into two per-half MUFUs + a PRMT anyway).
+template <int INPUT, bool PRECISE>
+__device__ __forceinline__ void recon8_t(const float (&xc)[8], const uint32_t (&dw)[4], uint32_t (&gw)[4], float s, float& acc,
+                                         float& prod) {
+  const float c = 0.5f * s, ms = -s;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float d2[2] = {__uint_as_float(dw[i] << 16), __uint_as_float(dw[i] & 0xffff0000u)};
+    float g2[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const float d = d2[j], x = xc[2 * i + j];
+      if (INPUT == DMVAE_INPUT_BINARY) {
+        const float h = 0.5f * fabsf(d);
+        float ua;
+        asm("tanh.approx.f32 %0, %1;" : "=f"(ua) : "f"(h));
+        const float u = __uint_as_float((__float_as_uint(d) & 0x80000000u) | __float_as_uint(ua));
+        g2[j] = fmaf(u, c, x * ms);                             // s (sigmoid(d) - x)
+        acc += h;
+        acc = fmaf(-d, x, acc);
+        if (PRECISE) {
+          float t;
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(h * -2.8853900817779268f));
+          prod = fmaf(prod, t, prod);
+        } else {
+          prod = fmaf(prod, ua, prod);
+        }
+      } else {
+        const float df = d - x;                                 // base_models.py:80-83 (x is not centred here)
+        g2[j] = s * df;
+        acc = fmaf(0.5f * df, df, acc);
+      }
+    }
+    __nv_bfloat162 gb = __floats2bfloat162_rn(g2[0], g2[1]);
+    gw[i] = *reinterpret_cast<uint32_t*>(&gb);
+  }
+}
+
+__device__ __forceinline__ float fast_exp(float x) {            // e^x, relative error ~2^-21 (ex2.approx on the XU pipe)
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));
+  return y;
+}
+
+template <typename TX, typename TD, int INPUT, bool PRECISE, int MINB>
+__global__ void __launch_bounds__(kFastThreads, MINB) elbo_rowtile_kernel(const ElboParams p) {
   extern __shared__ __align__(128) float smem[];
   constexpr bool FAST = sizeof(TD) == 2;
+  constexpr bool CENTRED = FAST && INPUT == DMVAE_INPUT_BINARY;   // the bf16-tier binary path works on x - 1/2
   const dmvae_elbo_args& a = p.a;
-  const int L = a.L, K = a.K, Ls = p.Ls, D = a.D;
-  const int Ks = K | 1;
-  const RowTileSmem sm(L, K, Ls, Ks);
-  float* tab_m = smem + sm.tab_m;             // [K][Ls]
-  float* tab_iv = smem + sm.tab_iv;           // [K][Ls] exp(-plv)
-  float* sum_plv = smem + sm.sum_plv;         // [K]
+  const int L = a.L, K = a.K, D = a.D;
+  const RowTileSmem sm(L, K);
   float* R_s = smem + sm.R;                   // [rows]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row0 = blockIdx.x * kFastRows;
@@ -605,50 +611,50 @@ __global__ void __launch_bounds__(kFastThreads, 3) elbo_rowtile_kernel(const Elb
     if (whole) asm volatile("bar.sync 3, 256;" ::: "memory");   // the barrier word is initialised before anyone polls it
     else __syncwarp();
     mbar_wait_parity(bar_w, 0);
+    // The warp's rows are ONE list of 8-element chunks, chunk c = lane + 32 i (no per-row tail iteration); a lane walks
+    // its chunks row by row, so the row sums are plain per-lane accumulators (no per-chunk row select).
     const int cpr = D >> 3;                                     // 8-element chunks per row (D % 8 == 0)
-    const int total = nrows_w * cpr;
-    float racc[kFastRW];
+    int c = lane;
 #pragma unroll
-    for (int q = 0; q < kFastRW; ++q) racc[q] = 0.f;
-    int rr = 0, cc = lane;
-    while (cc >= cpr) { cc -= cpr; ++rr; }
+    for (int q = 0; q < kFastRW; ++q) {
+      float acc = 0.f, prod = 1.f;
+      if (q < nrows_w) {
+        const int cend = (q + 1) * cpr;
+        uint32_t xa = xt_w + (uint32_t)(q * p.xrow + (c - q * cpr) * 8 * (int)sizeof(TX));
+        uint32_t da = dt_w + (uint32_t)(q * p.drow + (c - q * cpr) * 8 * (int)sizeof(TD));
 #pragma unroll 1
-    for (int c = lane; c < total; c += 32) {
-      const uint32_t xa = xt_w + (uint32_t)(rr * p.xrow + cc * 8 * (int)sizeof(TX));
-      const uint32_t da = dt_w + (uint32_t)(rr * p.drow + cc * 8 * (int)sizeof(TD));
-      float v;
-      if (FAST) {
-        __half2 xh[4];
-        uint32_t dw[4], gw[4];
-        tile8_half2<TX>(xa, xh);
-        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(dw[0]), "=r"(dw[1]), "=r"(dw[2]), "=r"(dw[3]) : "r"(da));
-        v = recon8_h2<INPUT>(xh, dw, gw, s_rec);
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(da), "r"(gw[0]), "r"(gw[1]), "r"(gw[2]), "r"(gw[3]) : "memory");
-      } else {
-        float x[8], d[8], g[8];
-        Tile8<TX>::load(xa, x);
-        Tile8<TD>::load(da, d);
-        v = 0.f;
+        for (; c < cend; c += 32, xa += 256u * (uint32_t)sizeof(TX), da += 256u * (uint32_t)sizeof(TD)) {
+          if (FAST) {
+            float x[8];
+            uint32_t dw[4], gw[4];
+            tile8_x<TX, CENTRED>(xa, x);
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(dw[0]), "=r"(dw[1]), "=r"(dw[2]), "=r"(dw[3]) : "r"(da));
+            recon8_t<INPUT, PRECISE>(x, dw, gw, s_rec, acc, prod);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(da), "r"(gw[0]), "r"(gw[1]), "r"(gw[2]), "r"(gw[3]) : "memory");
+          } else {
+            float x[8], d[8], g[8];
+            Tile8<TX>::load(xa, x);
+            Tile8<TD>::load(da, d);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v += recon1_rt<INPUT>(x[i], d[i], s_rec, g[i]);
-        Tile8<TD>::store(da, g);
+            for (int i = 0; i < 8; ++i) acc += recon1_rt<INPUT>(x[i], d[i], s_rec, g[i]);
+            Tile8<TD>::store(da, g);
+          }
+        }
       }
-#pragma unroll
-      for (int q = 0; q < kFastRW; ++q) racc[q] += (rr == q) ? v : 0.f;
-      cc += 32;
-      while (cc >= cpr) { cc -= cpr; ++rr; }
+      if (CENTRED) {                                            // + n ln 2 - ln prod(1 + u)   |   + ln prod(1 + t)
+        float lp;
+        asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lp) : "f"(prod));
+        acc = fmaf(lp, PRECISE ? 0.6931471805599453f : -0.6931471805599453f, acc);
+      }
+      float R = warp_sum(acc);
+      if (CENTRED && !PRECISE) R = fmaf((float)D, 0.6931471805599453f, R);
+      if (lane == 0) R_s[warp * kFastRW + q] = R;
     }
     // zero the padding columns [D, ddec_cols) of the gradient rows (operand of the decoder's dgrad / wgrad GEMMs)
     const int padw = (p.drow - D * (int)sizeof(TD)) >> 2;       // 32-bit words of padding per row
-    for (int i = lane; i < nrows_w * padw; i += 32) {
-      const int r2 = i / padw, j = i - r2 * padw;
-      asm volatile("st.shared.b32 [%0], %1;" ::"r"(dt_w + (uint32_t)(r2 * p.drow + D * (int)sizeof(TD) + 4 * j)), "r"(0u) : "memory");
-    }
-#pragma unroll
-    for (int q = 0; q < kFastRW; ++q) {
-      const float R = warp_sum(racc[q]);
-      if (lane == 0) R_s[warp * kFastRW + q] = R;
-    }
+    for (int q = 0; q < nrows_w; ++q)
+      for (int j = lane; j < padw; j += 32)
+        asm volatile("st.shared.b32 [%0], %1;" ::"r"(dt_w + (uint32_t)(q * p.drow + D * (int)sizeof(TD) + 4 * j)), "r"(0u) : "memory");
     asm volatile("bar.arrive 1, %0;" ::"n"(kFastThreads) : "memory");         // R_s written (latent warps wait on it)
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     if (whole) {
@@ -672,66 +678,59 @@ __global__ void __launch_bounds__(kFastThreads, 3) elbo_rowtile_kernel(const Elb
   }
 
   // =========================== latent warps: 8 rows each, four lanes per row ===========================
-  float* mu_s = smem + sm.mu;                 // [rows][Ls]
-  float* lv_s = smem + sm.lv;                 // [rows][Ls]
-  float* q_s = smem + sm.q;                   // [rows][Ks]
-  float* g_s = smem + sm.g;                   // [rows][Ks]
-  float* dmu_s = smem + sm.dmu;               // [rows][Ls]
-  float* dlv_s = smem + sm.dlv;               // [rows][Ls]
+  // Lane (row, h) owns the components k = h, h+4, ... in the first pass and the latent dimensions l = h, h+4, ... in
+  // the second; the row's inputs go global -> registers -> shared without index arithmetic, the gradients go from
+  // registers straight to global.  exp / log are single MUFU ops (ex2.approx / lg2.approx, ~2^-21 relative).
+  float2* tab = reinterpret_cast<float2*>(smem + sm.tab);       // [K][L] (m, exp(-plv))
+  float* sum_plv = smem + sm.sum_plv;                           // [K]
   const int lw = warp - 8;
-  const int lt = lw * 32 + lane;                                  // thread index among the latent warps
+  const int lt = lw * 32 + lane;                                // thread index among the latent warps
   constexpr int kLatThreads = 32 * kLatWarps;
-  constexpr int kRowsPerLat = kFastRows / kLatWarps;              // 8
-  const int lr0 = lw * kRowsPerLat;                               // first tile row of this warp
+  constexpr int kRowsPerLat = kFastRows / kLatWarps;            // 8
+  const int lr0 = lw * kRowsPerLat;                             // first tile row of this warp
   const int nrows_l = max(0, min(kRowsPerLat, nrows_cta - lr0));
-  // stage the prior tables (both latent warps) and this warp's latent inputs; all loads are issued before any use
-  for (int i = lt; i < K * L; i += kLatThreads) {
-    const int k = i / L, l = i - k * L;
-    tab_m[k * Ls + l] = __ldg(a.prior_means + i);
-    tab_iv[k * Ls + l] = expf(-__ldg(a.prior_log_vars + i));
-  }
+  const int rl = lr0 + (lane >> 2), h = lane & 3;
+  const bool valid = (lane >> 2) < nrows_l;
+  const int rsel = valid ? rl : 0;                              // idle lanes shadow the tile's first row (always present)
+  const int64_t grow = row0 + rsel;
+  float2* ml_r = reinterpret_cast<float2*>(smem + sm.ml) + rsel * L;
+  float* q_r = smem + sm.q + rsel * K;
+  float* g_r = smem + sm.g + rsel * K;
+  for (int i = lt; i < K * L; i += kLatThreads)
+    tab[i] = make_float2(__ldg(a.prior_means + i), fast_exp(-__ldg(a.prior_log_vars + i)));
   for (int k = lt; k < K; k += kLatThreads) {
     float sacc = 0.f;
     for (int l = 0; l < L; ++l) sacc += __ldg(a.prior_log_vars + k * L + l);
     sum_plv[k] = sacc;
   }
-  for (int i = lane; i < nrows_l * L; i += 32) {
-    const int rr = i / L, l = i - rr * L;
-    mu_s[(lr0 + rr) * Ls + l] = __ldg(a.mean + (int64_t)(row0 + lr0 + rr) * a.ld_zh + l);
-    lv_s[(lr0 + rr) * Ls + l] = __ldg(a.log_var + (int64_t)(row0 + lr0 + rr) * a.ld_zh + l);
+  float sum_lv = 0.f;
+  {
+    const float* mp = a.mean + grow * a.ld_zh;
+    const float* vp = a.log_var + grow * a.ld_zh;
+#pragma unroll 4
+    for (int l = h; l < L; l += 4) {
+      const float mu = __ldg(mp + l), lv = __ldg(vp + l);
+      if (valid) ml_r[l] = make_float2(mu, fast_exp(lv));
+      sum_lv += lv;
+    }
   }
-  for (int i = lane; i < nrows_l * K; i += 32) {
-    const int rr = i / K, k = i - rr * K;
-    q_s[(lr0 + rr) * Ks + k] = __ldg(a.logits + (int64_t)(row0 + lr0 + rr) * a.ld_logits + k);
+  float mx = -INFINITY;
+  int amax = K;
+  {
+    const float* lp = a.logits + grow * a.ld_logits;
+#pragma unroll 4
+    for (int k = h; k < K; k += 4) {
+      const float sc = __ldg(lp + k);
+      if (valid) q_r[k] = sc;
+      if (sc > mx) { mx = sc; amax = k; }                       // first maximum wins
+    }
   }
-  asm volatile("bar.sync 2, %0;" ::"n"(kLatThreads) : "memory");              // tables complete (latent warps only)
-
-  const int rl = lr0 + (lane >> 2), h = lane & 3;
-  const bool valid = (lane >> 2) < nrows_l;
-  const int rsel = valid ? rl : lr0;
-  const float logK = logf((float)K);
-  float* mu_r = mu_s + rsel * Ls;
-  float* elv_r = lv_s + rsel * Ls;
-  float* q_r = q_s + rsel * Ks;
-  float* g_r = g_s + rsel * Ks;
   auto quad_sum = [](float v) {
     v += __shfl_xor_sync(0xffffffffu, v, 1);
     v += __shfl_xor_sync(0xffffffffu, v, 2);
     return v;
   };
-  float sum_lv = 0.f;
-  for (int l = h; l < L; l += 4) {
-    const float lv = elv_r[l];
-    if (valid) elv_r[l] = expf(lv);
-    sum_lv += lv;
-  }
   sum_lv = quad_sum(sum_lv);
-  float mx = -INFINITY;
-  int amax = K;
-  for (int k = h; k < K; k += 4) {
-    const float sc = q_r[k];
-    if (sc > mx) { mx = sc; amax = k; }                         // first maximum wins
-  }
 #pragma unroll
   for (int o = 1; o <= 2; o <<= 1) {
     const float om = __shfl_xor_sync(0xffffffffu, mx, o);
@@ -739,52 +738,87 @@ __global__ void __launch_bounds__(kFastThreads, 3) elbo_rowtile_kernel(const Elb
     if (om > mx || (om == mx && oi < amax)) { mx = om; amax = oi; }
   }
   float den = 0.f;
-  for (int k = h; k < K; k += 4) {
-    const float e = expf(q_r[k] - mx);
-    if (valid) q_r[k] = e;
-    den += e;
-  }
-  den = quad_sum(den);
-  __syncwarp();                                                 // exp(lv) of all four lanes visible
-  const float inv_den = 1.f / den;
-  float C = 0.f, Zk = 0.f, qG = 0.f;
-  for (int k = h; k < K; k += 4) {
-    const float q = q_r[k] * inv_den;
-    const float* mk = tab_m + k * Ls;
-    const float* ik = tab_iv + k * Ls;
-    float acc = 0.f;
-    for (int l = 0; l < L; ++l) {
-      const float dm = mu_r[l] - mk[l];
-      acc += (elv_r[l] + dm * dm) * ik[l];
+  if (valid)
+    for (int k = h; k < K; k += 4) {
+      const float e = fast_exp(q_r[k] - mx);                    // own values: written by this thread above
+      q_r[k] = e;
+      den += e;
     }
-    const float A = sum_plv[k] - sum_lv - (float)L + acc;
-    const float lq = logf(q + kEps0);
-    C += q * (lq + logK);                                       // priors.py:195-199
-    const float gC = lq + q / (q + kEps0) + logK;
-    const float G = r * (gC + 0.5f * A);
-    Zk += 0.5f * q * A;
-    qG += q * G;
-    if (valid) { q_r[k] = q; g_r[k] = G; }
-  }
+  den = quad_sum(den);
+  const float inv_den = __fdividef(1.f, den);
+  asm volatile("bar.sync 2, %0;" ::"n"(kLatThreads) : "memory");              // prior tables and row inputs complete
+  const float logK = __logf((float)K);
+  float C = 0.f, Zk = 0.f, qG = 0.f, wsum = 0.f;
+  if (valid)
+    for (int k = h; k < K; k += 4) {
+      const float q = q_r[k] * inv_den;
+      const float2* tk = tab + k * L;
+      float acc = 0.f;
+#pragma unroll 2
+      for (int l = 0; l < L; ++l) {
+        const float2 t = tk[l], m = ml_r[l];
+        const float dm = m.x - t.x;
+        acc = fmaf(fmaf(dm, dm, m.y), t.y, acc);
+      }
+      const float A = sum_plv[k] - sum_lv - (float)L + acc;
+      const float lq = __logf(q + kEps0);
+      C = fmaf(q, lq + logK, C);                                // priors.py:195-199
+      const float gC = lq + __fdividef(q, q + kEps0) + logK;
+      const float G = r * fmaf(0.5f, A, gC);
+      Zk = fmaf(0.5f * q, A, Zk);
+      qG = fmaf(q, G, qG);
+      wsum += q;
+      q_r[k] = q;
+      g_r[k] = G;
+    }
   C = quad_sum(C);
   Zk = quad_sum(Zk);
   qG = quad_sum(qG);
-  for (int k = h; k < K; k += 4)
-    if (valid) g_r[k] = s * q_r[k] * (g_r[k] - qG);             // d loss / d logits_k
-  __syncwarp();                                                 // q of all four lanes visible
-  for (int l = h; l < L; l += 4) {
-    const float mu = mu_r[l];
-    float dmu = 0.f, wiv = 0.f, wsum = 0.f;
-    for (int k = 0; k < K; ++k) {
-      const float w = q_r[k], iv = tab_iv[k * Ls + l], mk = tab_m[k * Ls + l];
-      dmu += w * (mu - mk) * iv;
-      wiv += w * iv;
-      wsum += w;
+  wsum = quad_sum(wsum);
+  if (valid)
+    for (int k = h; k < K; k += 4) g_r[k] = s * q_r[k] * (g_r[k] - qG);       // d loss / d logits_k
+  __syncwarp();                                                 // q, d_logits of all four lanes visible
+  if (valid) {
+    float* dmp = a.d_mean_kl + grow * a.ld_dkl;
+    float* dvp = a.d_log_var_kl + grow * a.ld_dkl;
+    const float sr = s * r;
+    for (int l = h; l < L; l += 4) {
+      const float2 m = ml_r[l];
+      float dmu = 0.f, wiv = 0.f;
+#pragma unroll 2
+      for (int k = 0; k < K; ++k) {
+        const float2 t = tab[k * L + l];
+        const float wi = q_r[k] * t.y;
+        wiv += wi;
+        dmu = fmaf(wi, m.x - t.x, dmu);
+      }
+      dmp[l] = sr * dmu;
+      dvp[l] = sr * 0.5f * fmaf(m.y, wiv, -wsum);
     }
-    if (valid) {
-      dmu_s[rl * Ls + l] = s * r * dmu;
-      dlv_s[rl * Ls + l] = s * r * 0.5f * (elv_r[l] * wiv - wsum);
+    // d_logits row [K data | zeros to dlogits_cols]
+    if (a.dlogits_dtype == DMVAE_BF16 && (a.dlogits_cols & 7) == 0 && (a.ld_dlogits & 7) == 0) {
+      __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(a.d_logits) + grow * a.ld_dlogits;
+      for (int c8 = h << 3; c8 < a.dlogits_cols; c8 += 32) {
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = (c8 + j < K) ? g_r[c8 + j] : 0.f;
+        Vec8<__nv_bfloat16>::store(out + c8, v);
+      }
+    } else {
+      for (int c = h; c < a.dlogits_cols; c += 4) {
+        const float v = c < K ? g_r[c] : 0.f;
+        if (a.dlogits_dtype == DMVAE_BF16)
+          reinterpret_cast<__nv_bfloat16*>(a.d_logits)[grow * a.ld_dlogits + c] = __float2bfloat16_rn(v);
+        else
+          reinterpret_cast<float*>(a.d_logits)[grow * a.ld_dlogits + c] = v;
+      }
     }
+  }
+  // q(c|x) of this warp's rows: one flat coalesced copy
+  {
+    const float* qs = smem + sm.q + lr0 * K;
+    float* qo = a.qc + (int64_t)(row0 + lr0) * K;
+    for (int i = lane; i < nrows_l * K; i += 32) qo[i] = qs[i];
   }
   asm volatile("bar.sync 1, %0;" ::"n"(kFastThreads) : "memory");             // every slab's R_s is written
   if (valid && h == 0) {
@@ -792,42 +826,10 @@ __global__ void __launch_bounds__(kFastThreads, 3) elbo_rowtile_kernel(const Elb
     reinterpret_cast<float4*>(a.per_sample)[row0 + rl] = make_float4(R, C, Zk, a.recon_scale * R + r * (C + Zk));
     a.argmax[row0 + rl] = amax;
   }
-  __syncwarp();
-  // ---- write-out of this warp's rows ----
-  for (int i = lane; i < nrows_l * K; i += 32) {
-    const int rr = lr0 + i / K, k = i % K;
-    a.qc[(int64_t)(row0 + rr) * K + k] = q_s[rr * Ks + k];
-  }
-  for (int i = lane; i < nrows_l * L; i += 32) {
-    const int rr = lr0 + i / L, l = i % L;
-    a.d_mean_kl[(int64_t)(row0 + rr) * a.ld_dkl + l] = dmu_s[rr * Ls + l];
-    a.d_log_var_kl[(int64_t)(row0 + rr) * a.ld_dkl + l] = dlv_s[rr * Ls + l];
-  }
-  // d_logits rows [K data | zeros to dlogits_cols] in 16-byte pieces
-  if (a.dlogits_dtype == DMVAE_BF16 && (a.dlogits_cols & 7) == 0 && (a.ld_dlogits & 7) == 0) {
-    const int cpr = a.dlogits_cols >> 3;
-    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(a.d_logits);
-    for (int i = lane; i < nrows_l * cpr; i += 32) {
-      const int rr = lr0 + i / cpr, c8 = (i % cpr) << 3;
-      float v[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = (c8 + j < K) ? g_s[rr * Ks + c8 + j] : 0.f;
-      Vec8<__nv_bfloat16>::store(out + (int64_t)(row0 + rr) * a.ld_dlogits + c8, v);
-    }
-  } else {
-    for (int i = lane; i < nrows_l * a.dlogits_cols; i += 32) {
-      const int rr = lr0 + i / a.dlogits_cols, c = i % a.dlogits_cols;
-      const float v = c < K ? g_s[rr * Ks + c] : 0.f;
-      if (a.dlogits_dtype == DMVAE_BF16)
-        reinterpret_cast<__nv_bfloat16*>(a.d_logits)[(int64_t)(row0 + rr) * a.ld_dlogits + c] = __float2bfloat16_rn(v);
-      else
-        reinterpret_cast<float*>(a.d_logits)[(int64_t)(row0 + rr) * a.ld_dlogits + c] = v;
-    }
-  }
 }
 
 size_t elbo_rowtile_smem_bytes(const ElboParams& p) {
-  const size_t fl = (sizeof(float) * (size_t)RowTileSmem(p.a.L, p.a.K, p.Ls, p.a.K | 1).total + 127) & ~(size_t)127;
+  const size_t fl = (sizeof(float) * (size_t)RowTileSmem(p.a.L, p.a.K).total + 127) & ~(size_t)127;
   return fl + 128 + (size_t)kFastRows * (size_t)(p.xrow + p.drow);
 }
 
@@ -846,7 +848,21 @@ bool elbo_rowtile_ok(const ElboParams& p) {
 template <typename TX, typename TD, int INPUT>
 int launch_elbo_rowtile(dmvae_ctx* ctx, const ElboParams& p, cudaStream_t st) {
   const size_t smem = elbo_rowtile_smem_bytes(p);
-  auto kern = elbo_rowtile_kernel<TX, TD, INPUT>;
+  static int precise = -1;                    // DMVAE_ELBO_PRECISE=1: second MUFU (ex2) for the log term of the bf16 tier
+  if (precise < 0) {
+    const char* e = getenv("DMVAE_ELBO_PRECISE");
+    precise = (e && e[0] == '1') ? 1 : 0;
+  }
+  constexpr bool kHasPrecise = sizeof(TD) == 2 && INPUT == DMVAE_INPUT_BINARY;
+  static int minb = -1;
+  if (minb < 0) {
+    const char* e = getenv("DMVAE_ELBO_MINB");
+    minb = e ? atoi(e) : 4;
+  }
+  auto kern = elbo_rowtile_kernel<TX, TD, INPUT, false, 4>;
+  if (minb == 3) kern = elbo_rowtile_kernel<TX, TD, INPUT, false, 3>;
+  if (minb == 5) kern = elbo_rowtile_kernel<TX, TD, INPUT, false, 5>;
+  if (kHasPrecise && precise) kern = elbo_rowtile_kernel<TX, TD, INPUT, kHasPrecise, 4>;
   if (smem > 48 * 1024) DMVAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int blocks = (p.a.rows + kFastRows - 1) / kFastRows;
   dmvae_launch(kern, dim3(blocks), dim3(kFastThreads), smem, st, true, p);

@@ -26,6 +26,8 @@ def main():
     ap.add_argument("--L", type=int, default=10)
     ap.add_argument("--K", type=int, default=10)
     ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--check", action="store_true", help="report the error of the reconstruction term and of d_decoded against "
+                    "torch fp64 on the same bf16 logits (randn logits and trained-like saturated logits)")
     args = ap.parse_args()
     peak = 6545.9
     pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -71,6 +73,20 @@ def main():
         for ea in eas:
             _abi.check(lib.dmvae_elbo_fwd_bwd(ctx, C.byref(ea), st()))
         torch.cuda.synchronize()
+        if args.check:
+            X, dec, ddec = sets[0]
+            for name in ("randn*2", "trained-like"):
+                if name == "trained-like":                       # confident logits that mostly agree with the targets
+                    dec[:, :D] = ((X.float() * 2 - 1) * (6 + 3 * torch.randn(B, D, device="cuda"))).to(torch.bfloat16)
+                _abi.check(lib.dmvae_elbo_fwd_bwd(ctx, C.byref(eas[0]), st()))
+                torch.cuda.synchronize()
+                d64, x64 = dec[:, :D].double(), X.double()
+                R = (torch.nn.functional.softplus(d64) - d64 * x64).sum(1)
+                g = (torch.sigmoid(d64) - x64) / B
+                eR = ((ps[:, 0].double() - R).abs() / R.abs()).max().item()
+                eg = (ddec[:, :D].double() - g).abs().max().item() * B
+                print("  check %-12s rows %d: recon term max rel err %.2e (mean R %.1f), d_decoded max abs err %.2e x 1/B"
+                      % (name, B, eR, R.mean().item(), eg))
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
             for i in range(args.iters):
