@@ -445,7 +445,7 @@ struct RowTileSmem {
   int tab, sum_plv, ml, q, g, R, total;
   __host__ __device__ RowTileSmem(int L, int K) {
     int o = 0;
-    tab = o; o += 2 * K * L;                // float2 (prior mean, exp(-prior log-variance)) [K][L]
+    tab = o; o += 2 * K * ((L + 3) & ~3);   // float2 (prior mean, exp(-prior log-variance)) [K][L | padded to 4 LQ]
     sum_plv = o; o += (K + 3) & ~3;
     ml = o; o += 2 * kFastRows * L;         // float2 (mean, exp(log_var)) [rows][L]
     q = o; o += (kFastRows * K + 3) & ~3;   // logits -> q(c|x), [rows][K]
@@ -555,8 +555,190 @@ __device__ __forceinline__ float fast_exp(float x) {            // e^x, relative
   return y;
 }
 
-template <typename TX, typename TD, int INPUT, bool PRECISE, int MINB>
-__global__ void __launch_bounds__(kFastThreads, MINB) elbo_rowtile_kernel(const ElboParams p) {
+// d_logits row [K data | zeros to dlogits_cols], written by the four lanes of a row's quad
+__device__ __forceinline__ void rowtile_store_dlogits(const dmvae_elbo_args& a, const float* g_r, int64_t grow, int h, int K) {
+  if (a.dlogits_dtype == DMVAE_BF16 && (a.dlogits_cols & 7) == 0 && (a.ld_dlogits & 7) == 0) {
+    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(a.d_logits) + grow * a.ld_dlogits;
+    for (int c8 = h << 3; c8 < a.dlogits_cols; c8 += 32) {
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = (c8 + j < K) ? g_r[c8 + j] : 0.f;
+      Vec8<__nv_bfloat16>::store(out + c8, v);
+    }
+  } else {
+    for (int c = h; c < a.dlogits_cols; c += 4) {
+      const float v = c < K ? g_r[c] : 0.f;
+      if (a.dlogits_dtype == DMVAE_BF16)
+        reinterpret_cast<__nv_bfloat16*>(a.d_logits)[grow * a.ld_dlogits + c] = __float2bfloat16_rn(v);
+      else
+        reinterpret_cast<float*>(a.d_logits)[grow * a.ld_dlogits + c] = v;
+    }
+  }
+}
+
+// q(c|x) of a latent warp's rows: one flat coalesced copy
+__device__ __forceinline__ void rowtile_store_q(const dmvae_elbo_args& a, const float* qs, int row_first, int n, int lane) {
+  float* qo = a.qc + (int64_t)row_first * a.K;
+  for (int i = lane; i < n; i += 32) qo[i] = qs[i];
+}
+
+// Latent part of the row-tile kernel for L <= 4 LQ (register-resident): lane (row, h) of a quad owns the latent
+// dimensions l = h + 4 j, j < LQ (mean, exp(log_var), d_mean, sum_k w iv in registers) and ONE sweep over the K
+// components produces both A_k (quad-reduced) and the KL-side gradients - q = softmax(logits) does not depend on A, so
+// the two passes of the formulas (SURVEY 8a') fuse.  The prior table is zero-padded to 4 LQ columns: padded (l >= L)
+// entries contribute exact zeros.  ~7 issue slots per (k, l) pair instead of ~20 for the generic two-pass loops.
+template <int LQ>
+__device__ __forceinline__ void rowtile_latent(const dmvae_elbo_args& a, float* smem, const RowTileSmem& sm, int row0,
+                                               int nrows_cta, int lw, int lane, float r, float s) {
+  constexpr int Ls = 4 * LQ;
+  constexpr int kLatThreads = 32 * kLatWarps;
+  constexpr int kRowsPerLat = kFastRows / kLatWarps;
+  const int L = a.L, K = a.K;
+  float2* tab = reinterpret_cast<float2*>(smem + sm.tab);       // [K][Ls] (m, exp(-plv)), zero beyond L
+  float* sum_plv = smem + sm.sum_plv;
+  const float* R_s = smem + sm.R;
+  const int lt = lw * 32 + lane;
+  const int lr0 = lw * kRowsPerLat;
+  const int nrows_l = max(0, min(kRowsPerLat, nrows_cta - lr0));
+  const int rl = lr0 + (lane >> 2), h = lane & 3;
+  const bool valid = (lane >> 2) < nrows_l;
+  const int rsel = valid ? rl : 0;                              // idle lanes shadow the tile's first row (always present)
+  const int64_t grow = row0 + rsel;
+  float* q_r = smem + sm.q + rsel * K;
+  float* g_r = smem + sm.g + rsel * K;
+  for (int i = lt; i < K * Ls; i += kLatThreads) {
+    const int k = i / Ls, l = i - k * Ls;
+    float2 t = make_float2(0.f, 0.f);
+    if (l < L) t = make_float2(__ldg(a.prior_means + k * L + l), fast_exp(-__ldg(a.prior_log_vars + k * L + l)));
+    tab[i] = t;
+  }
+  for (int k = lt; k < K; k += kLatThreads) {
+    float sacc = 0.f;
+    for (int l = 0; l < L; ++l) sacc += __ldg(a.prior_log_vars + k * L + l);
+    sum_plv[k] = sacc;
+  }
+  float mu[LQ], elv[LQ], sum_lv = 0.f;
+  {
+    const float* mp = a.mean + grow * a.ld_zh;
+    const float* vp = a.log_var + grow * a.ld_zh;
+    float lv[LQ];
+#pragma unroll
+    for (int j = 0; j < LQ; ++j) {
+      const int l = h + 4 * j;
+      mu[j] = l < L ? __ldg(mp + l) : 0.f;
+      lv[j] = l < L ? __ldg(vp + l) : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < LQ; ++j) {
+      elv[j] = (h + 4 * j < L) ? fast_exp(lv[j]) : 0.f;
+      sum_lv += lv[j];
+    }
+  }
+  float mx = -INFINITY;
+  int amax = K;
+  {
+    const float* lp = a.logits + grow * a.ld_logits;
+#pragma unroll 4
+    for (int k = h; k < K; k += 4) {
+      const float sc = __ldg(lp + k);
+      if (valid) q_r[k] = sc;
+      if (sc > mx) { mx = sc; amax = k; }                       // first maximum wins
+    }
+  }
+  auto quad_sum = [](float v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    return v;
+  };
+  sum_lv = quad_sum(sum_lv);
+#pragma unroll
+  for (int o = 1; o <= 2; o <<= 1) {
+    const float om = __shfl_xor_sync(0xffffffffu, mx, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, amax, o);
+    if (om > mx || (om == mx && oi < amax)) { mx = om; amax = oi; }
+  }
+  float den = 0.f;
+  if (valid)
+    for (int k = h; k < K; k += 4) {
+      const float e = fast_exp(q_r[k] - mx);                    // own values: written by this thread above
+      q_r[k] = e;
+      den += e;
+    }
+  den = quad_sum(den);
+  const float inv_den = __fdividef(1.f, den);
+  asm volatile("bar.sync 2, %0;" ::"n"(kLatThreads) : "memory");              // prior tables and exp(logit - max) complete
+  // ---- one sweep over the components ----
+  float dmu[LQ], wiv[LQ];
+#pragma unroll
+  for (int j = 0; j < LQ; ++j) dmu[j] = wiv[j] = 0.f;
+  {
+    const float2* tk = tab + h;
+#pragma unroll 2
+    for (int k = 0; k < K; ++k, tk += Ls) {
+      const float qk = q_r[k] * inv_den;
+      float accA = 0.f;
+#pragma unroll
+      for (int j = 0; j < LQ; ++j) {
+        const float2 t = tk[4 * j];
+        const float dm = mu[j] - t.x;
+        accA = fmaf(fmaf(dm, dm, elv[j]), t.y, accA);
+        const float wi = qk * t.y;
+        wiv[j] += wi;
+        dmu[j] = fmaf(wi, dm, dmu[j]);
+      }
+      accA = quad_sum(accA);
+      if (valid && h == (k & 3)) g_r[k] = accA;                 // read back below by the same lane
+    }
+  }
+  __syncwarp();                                                 // the sweep's reads of exp(logit - max) are done
+  const float logK = __logf((float)K);
+  float C = 0.f, Zk = 0.f, qG = 0.f, wsum = 0.f;
+  if (valid)
+    for (int k = h; k < K; k += 4) {
+      const float q = q_r[k] * inv_den;
+      const float A = sum_plv[k] - sum_lv - (float)L + g_r[k];
+      const float lq = __logf(q + kEps0);
+      C = fmaf(q, lq + logK, C);                                // priors.py:195-199
+      const float gC = lq + __fdividef(q, q + kEps0) + logK;
+      const float G = r * fmaf(0.5f, A, gC);
+      Zk = fmaf(0.5f * q, A, Zk);
+      qG = fmaf(q, G, qG);
+      wsum += q;
+      q_r[k] = q;
+      g_r[k] = G;
+    }
+  C = quad_sum(C);
+  Zk = quad_sum(Zk);
+  qG = quad_sum(qG);
+  wsum = quad_sum(wsum);
+  if (valid)
+    for (int k = h; k < K; k += 4) g_r[k] = s * q_r[k] * (g_r[k] - qG);       // d loss / d logits_k
+  __syncwarp();                                                 // q, d_logits of all four lanes visible
+  if (valid) {
+    float* dmp = a.d_mean_kl + grow * a.ld_dkl;
+    float* dvp = a.d_log_var_kl + grow * a.ld_dkl;
+    const float sr = s * r;
+#pragma unroll
+    for (int j = 0; j < LQ; ++j) {
+      const int l = h + 4 * j;
+      if (l < L) {
+        dmp[l] = sr * dmu[j];
+        dvp[l] = sr * 0.5f * fmaf(elv[j], wiv[j], -wsum);
+      }
+    }
+    rowtile_store_dlogits(a, g_r, grow, h, K);
+  }
+  rowtile_store_q(a, smem + sm.q + lr0 * K, row0 + lr0, nrows_l * K, lane);
+  asm volatile("bar.sync 1, %0;" ::"n"(kFastThreads) : "memory");             // every slab's R_s is written
+  if (valid && h == 0) {
+    const float R = R_s[rl];
+    reinterpret_cast<float4*>(a.per_sample)[row0 + rl] = make_float4(R, C, Zk, a.recon_scale * R + r * (C + Zk));
+    a.argmax[row0 + rl] = amax;
+  }
+}
+
+template <typename TX, typename TD, int INPUT, bool PRECISE>
+__global__ void __launch_bounds__(kFastThreads, 4) elbo_rowtile_kernel(const ElboParams p) {
   extern __shared__ __align__(128) float smem[];
   constexpr bool FAST = sizeof(TD) == 2;
   constexpr bool CENTRED = FAST && INPUT == DMVAE_INPUT_BINARY;   // the bf16-tier binary path works on x - 1/2
@@ -611,42 +793,59 @@ __global__ void __launch_bounds__(kFastThreads, MINB) elbo_rowtile_kernel(const 
     if (whole) asm volatile("bar.sync 3, 256;" ::: "memory");   // the barrier word is initialised before anyone polls it
     else __syncwarp();
     mbar_wait_parity(bar_w, 0);
-    // The warp's rows are ONE list of 8-element chunks, chunk c = lane + 32 i (no per-row tail iteration); a lane walks
-    // its chunks row by row, so the row sums are plain per-lane accumulators (no per-chunk row select).
+    // The warp's two rows are ONE list of 8-element chunks, chunk c = lane + 32 i (no per-row tail iteration).  A lane's
+    // chunks are ordered by row, so the row sums are plain per-lane accumulators that are parked once, at the
+    // iteration where the lane crosses into the second row.
+    static_assert(kFastRW == 2, "the reconstruction loop parks exactly one row");
     const int cpr = D >> 3;                                     // 8-element chunks per row (D % 8 == 0)
+    const int total = nrows_w * cpr;
+    const uint32_t dgap = (uint32_t)(p.drow - D * (int)sizeof(TD));           // the targets tile has no row gap
+    float acc = 0.f, prod = 1.f, acc0 = 0.f, prod0 = 1.f;
+    bool second = false;
+    uint32_t xa = xt_w + (uint32_t)(lane * 8 * (int)sizeof(TX));
+    uint32_t da = dt_w + (uint32_t)(lane * 8 * (int)sizeof(TD));
+    // three phases with ONE copy of the loop body: iterations where every lane is in the first row, the mixed
+    // iteration, the rest (second row); lanes park between phases, so the body carries no row logic
+    const int nA32 = (cpr >> 5) << 5;
     int c = lane;
+#pragma unroll 1
+    for (int ph = 0; ph < 3; ++ph) {
+      const int cstop = min(total, ph == 0 ? nA32 : (ph == 1 ? nA32 + 32 : total));
+      if (c >= cpr && !second) {
+        second = true;
+        acc0 = acc; prod0 = prod;
+        acc = 0.f; prod = 1.f;
+        da += dgap;
+      }
+#pragma unroll 1
+    for (; c < cstop; c += 32, xa += 256u * (uint32_t)sizeof(TX), da += 256u * (uint32_t)sizeof(TD)) {
+      if (FAST) {
+        float x[8];
+        uint32_t dw[4], gw[4];
+        tile8_x<TX, CENTRED>(xa, x);
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(dw[0]), "=r"(dw[1]), "=r"(dw[2]), "=r"(dw[3]) : "r"(da));
+        recon8_t<INPUT, PRECISE>(x, dw, gw, s_rec, acc, prod);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(da), "r"(gw[0]), "r"(gw[1]), "r"(gw[2]), "r"(gw[3]) : "memory");
+      } else {
+        float x[8], d[8], g[8];
+        Tile8<TX>::load(xa, x);
+        Tile8<TD>::load(da, d);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc += recon1_rt<INPUT>(x[i], d[i], s_rec, g[i]);
+        Tile8<TD>::store(da, g);
+      }
+    }
+    }
+    if (!second) { acc0 = acc; prod0 = prod; acc = 0.f; prod = 1.f; }         // the lane never reached the second row
 #pragma unroll
     for (int q = 0; q < kFastRW; ++q) {
-      float acc = 0.f, prod = 1.f;
-      if (q < nrows_w) {
-        const int cend = (q + 1) * cpr;
-        uint32_t xa = xt_w + (uint32_t)(q * p.xrow + (c - q * cpr) * 8 * (int)sizeof(TX));
-        uint32_t da = dt_w + (uint32_t)(q * p.drow + (c - q * cpr) * 8 * (int)sizeof(TD));
-#pragma unroll 1
-        for (; c < cend; c += 32, xa += 256u * (uint32_t)sizeof(TX), da += 256u * (uint32_t)sizeof(TD)) {
-          if (FAST) {
-            float x[8];
-            uint32_t dw[4], gw[4];
-            tile8_x<TX, CENTRED>(xa, x);
-            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(dw[0]), "=r"(dw[1]), "=r"(dw[2]), "=r"(dw[3]) : "r"(da));
-            recon8_t<INPUT, PRECISE>(x, dw, gw, s_rec, acc, prod);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(da), "r"(gw[0]), "r"(gw[1]), "r"(gw[2]), "r"(gw[3]) : "memory");
-          } else {
-            float x[8], d[8], g[8];
-            Tile8<TX>::load(xa, x);
-            Tile8<TD>::load(da, d);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) acc += recon1_rt<INPUT>(x[i], d[i], s_rec, g[i]);
-            Tile8<TD>::store(da, g);
-          }
-        }
-      }
+      float av = q == 0 ? acc0 : acc;
       if (CENTRED) {                                            // + n ln 2 - ln prod(1 + u)   |   + ln prod(1 + t)
         float lp;
-        asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lp) : "f"(prod));
-        acc = fmaf(lp, PRECISE ? 0.6931471805599453f : -0.6931471805599453f, acc);
+        asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lp) : "f"(q == 0 ? prod0 : prod));
+        av = fmaf(lp, PRECISE ? 0.6931471805599453f : -0.6931471805599453f, av);
       }
-      float R = warp_sum(acc);
+      float R = warp_sum(av);
       if (CENTRED && !PRECISE) R = fmaf((float)D, 0.6931471805599453f, R);
       if (lane == 0) R_s[warp * kFastRW + q] = R;
     }
@@ -681,9 +880,18 @@ __global__ void __launch_bounds__(kFastThreads, MINB) elbo_rowtile_kernel(const 
   // Lane (row, h) owns the components k = h, h+4, ... in the first pass and the latent dimensions l = h, h+4, ... in
   // the second; the row's inputs go global -> registers -> shared without index arithmetic, the gradients go from
   // registers straight to global.  exp / log are single MUFU ops (ex2.approx / lg2.approx, ~2^-21 relative).
+  const int lw = warp - 8;
+  if (L <= 16) {                                                // register-resident fused sweep
+    const int lq = (L + 3) >> 2;
+    if (lq == 1) rowtile_latent<1>(a, smem, sm, row0, nrows_cta, lw, lane, r, s);
+    else if (lq == 2) rowtile_latent<2>(a, smem, sm, row0, nrows_cta, lw, lane, r, s);
+    else if (lq == 3) rowtile_latent<3>(a, smem, sm, row0, nrows_cta, lw, lane, r, s);
+    else rowtile_latent<4>(a, smem, sm, row0, nrows_cta, lw, lane, r, s);
+    return;
+  }
+  // generic two-pass form (any L <= 64)
   float2* tab = reinterpret_cast<float2*>(smem + sm.tab);       // [K][L] (m, exp(-plv))
   float* sum_plv = smem + sm.sum_plv;                           // [K]
-  const int lw = warp - 8;
   const int lt = lw * 32 + lane;                                // thread index among the latent warps
   constexpr int kLatThreads = 32 * kLatWarps;
   constexpr int kRowsPerLat = kFastRows / kLatWarps;            // 8
@@ -795,31 +1003,9 @@ __global__ void __launch_bounds__(kFastThreads, MINB) elbo_rowtile_kernel(const 
       dmp[l] = sr * dmu;
       dvp[l] = sr * 0.5f * fmaf(m.y, wiv, -wsum);
     }
-    // d_logits row [K data | zeros to dlogits_cols]
-    if (a.dlogits_dtype == DMVAE_BF16 && (a.dlogits_cols & 7) == 0 && (a.ld_dlogits & 7) == 0) {
-      __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(a.d_logits) + grow * a.ld_dlogits;
-      for (int c8 = h << 3; c8 < a.dlogits_cols; c8 += 32) {
-        float v[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = (c8 + j < K) ? g_r[c8 + j] : 0.f;
-        Vec8<__nv_bfloat16>::store(out + c8, v);
-      }
-    } else {
-      for (int c = h; c < a.dlogits_cols; c += 4) {
-        const float v = c < K ? g_r[c] : 0.f;
-        if (a.dlogits_dtype == DMVAE_BF16)
-          reinterpret_cast<__nv_bfloat16*>(a.d_logits)[grow * a.ld_dlogits + c] = __float2bfloat16_rn(v);
-        else
-          reinterpret_cast<float*>(a.d_logits)[grow * a.ld_dlogits + c] = v;
-      }
-    }
+    rowtile_store_dlogits(a, g_r, grow, h, K);
   }
-  // q(c|x) of this warp's rows: one flat coalesced copy
-  {
-    const float* qs = smem + sm.q + lr0 * K;
-    float* qo = a.qc + (int64_t)(row0 + lr0) * K;
-    for (int i = lane; i < nrows_l * K; i += 32) qo[i] = qs[i];
-  }
+  rowtile_store_q(a, smem + sm.q + lr0 * K, row0 + lr0, nrows_l * K, lane);
   asm volatile("bar.sync 1, %0;" ::"n"(kFastThreads) : "memory");             // every slab's R_s is written
   if (valid && h == 0) {
     const float R = R_s[rl];
@@ -854,15 +1040,8 @@ int launch_elbo_rowtile(dmvae_ctx* ctx, const ElboParams& p, cudaStream_t st) {
     precise = (e && e[0] == '1') ? 1 : 0;
   }
   constexpr bool kHasPrecise = sizeof(TD) == 2 && INPUT == DMVAE_INPUT_BINARY;
-  static int minb = -1;
-  if (minb < 0) {
-    const char* e = getenv("DMVAE_ELBO_MINB");
-    minb = e ? atoi(e) : 4;
-  }
-  auto kern = elbo_rowtile_kernel<TX, TD, INPUT, false, 4>;
-  if (minb == 3) kern = elbo_rowtile_kernel<TX, TD, INPUT, false, 3>;
-  if (minb == 5) kern = elbo_rowtile_kernel<TX, TD, INPUT, false, 5>;
-  if (kHasPrecise && precise) kern = elbo_rowtile_kernel<TX, TD, INPUT, kHasPrecise, 4>;
+  auto kern = elbo_rowtile_kernel<TX, TD, INPUT, false>;
+  if (kHasPrecise && precise) kern = elbo_rowtile_kernel<TX, TD, INPUT, kHasPrecise>;
   if (smem > 48 * 1024) DMVAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int blocks = (p.a.rows + kFastRows - 1) / kFastRows;
   dmvae_launch(kern, dim3(blocks), dim3(kFastThreads), smem, st, true, p);
