@@ -833,6 +833,8 @@ class Engine:
                     self._dz_cleared = False
                     self._dgrad(nm, dy, dy.stride(0), None, 0, self.dz, F32, rows, self.L, self.dz.shape[1], split_k=sk)
                 self._flush_group()
+                if i == 1:                           # the decoder above its first layer is final (+ the prior tables)
+                    self._adam_segment(chain[1:] + ["decx", "priors"])
         # data parallel: the decoder's gradients are complete - exchange them while the encoder's backward runs
         dpo = getattr(self, "_dp_opt", None)
         if (self.dp is not None and dpo is not None and getattr(self.dp, "overlap_decoder", False) and through_decoder
@@ -861,6 +863,7 @@ class Engine:
                 self._wgrad("ch", h[:, hp:], h.stride(0), self.dch, self.dch.stride(0), rows)
                 self._dgrad("ch", self.dch, self.dch.stride(0), h[:, hp:], h.stride(0), dh[:, hp:], dt, rows, hv, hp)
             self._flush_group()                      # both heads' four GEMMs: one launch
+            self._adam_segment(["zh", "ch", chain[0]] + ([] if len(chain) > 1 else ["decx", "priors"]))
             a_in = self.act[self.enc_chain[-1]]
             if train_z and train_c:
                 self._wgrad("ench", a_in, a_in.stride(0), dh, dh.stride(0), rows)
@@ -879,6 +882,7 @@ class Engine:
                     self._dgrad("ench", dh[:, c0:], dh.stride(0), a_in, a_in.stride(0), self.dact[self.enc_chain[-1]], dt,
                                 rows, lp.n_valid, lp.n_block, W=Wsub, ldw=self.layers["ench"].out_pad, n_out_pad=hp)
             self._flush_group()
+            self._adam_segment(["ench"])
         else:
             if train_z:
                 a_in = self.act[self.enc_chain[-1]]
@@ -887,6 +891,7 @@ class Engine:
                 self._dgrad("zh", self.dzh, self.dzh.stride(0), a_in, a_in.stride(0), self.dact[self.enc_chain[-1]], dt,
                             rows, lp.n_valid, lp.n_block)
                 self._flush_group()
+                self._adam_segment(["zh", chain[0]] + ([] if len(chain) > 1 else ["decx", "priors"]))
         # ---- encoder trunk ----
         if train_trunk:
             ec = self.enc_chain
@@ -900,6 +905,8 @@ class Engine:
                     self._dgrad(nm, dy, dy.stride(0), a_in, a_in.stride(0), self.dact[ec[i - 1]], dt, rows, lp.n_valid,
                                 lp.n_block)
                 self._flush_group()
+                if i > 0:
+                    self._adam_segment([nm])
         self._end_group()
         self._join()
 
@@ -925,6 +932,57 @@ class Engine:
         self._toc("adam", t0)
         if zero_grads:
             self._grads_dirty = False
+
+    # ---- streamed update: Adam runs on a layer block as soon as that block's weight gradient is final (and the data
+    #      gradient that reads the block's bf16 operand copy is done), on the side stream beside the remaining gradient
+    #      GEMMs - those are bound by operand delivery from L2, the update by HBM, so the two overlap almost freely and
+    #      only the first encoder layer's block is left for the tail of the step.  Captured (device-scalar) steps only.
+    #      DMVAE_STREAM_ADAM=0 restores the single update at the end. ----
+    stream_adam = os.environ.get("DMVAE_STREAM_ADAM", "1") != "0"
+    _adam_live = None              # (AdamState, [(offset, n) already updated]) while a captured step streams its update
+
+    def _adam_range(self, opt: AdamState, off: int, n: int):
+        _abi.check(self.lib.dmvae_adam(self.ctx, self.params.data_ptr() + 4 * off, self.grads.data_ptr() + 4 * off,
+                                       opt.m.data_ptr() + 4 * off, opt.v.data_ptr() + 4 * off,
+                                       (self.params_op.data_ptr() + 2 * off) if self.params_op is not None else None,
+                                       n, 0.0, opt.state_dev.data_ptr() + 12, opt.beta1, opt.beta2, opt.eps, 1.0, 1,
+                                       self._stream()))
+
+    def _block_range(self, name: str) -> Tuple[int, int]:
+        if name == "priors":
+            return self.layout.off_means, 2 * self.layout.tab_size
+        ly = self.layers[name]
+        return ly.offset, ly.size
+
+    def _adam_segment(self, names):
+        """Blocks `names` are final: update them now on the side stream (contiguous blocks share one launch)."""
+        if self._adam_live is None:
+            return
+        opt, done = self._adam_live
+        merged = []
+        for off, n in sorted(self._block_range(nm) for nm in names):
+            if merged and merged[-1][0] + merged[-1][1] == off:
+                merged[-1] = (merged[-1][0], merged[-1][1] + n)
+            else:
+                merged.append((off, n))
+
+        def run():
+            for off, n in merged:
+                self._adam_range(opt, off, n)
+
+        self._fork(run)
+        done.extend(merged)
+
+    def _adam_rest(self, opt: AdamState):
+        """The blocks no segment covered (the tail of the step)."""
+        done = sorted(self._adam_live[1])
+        self._adam_live = None
+        pos = 0
+        for off, n in done + [(self.n_params, 0)]:
+            if off > pos:
+                self._adam_range(opt, pos, off - pos)
+            pos = max(pos, off + n)
+        self._grads_dirty = False
 
     # ------------------------------------------------------------------------------------------
     # whole steps
@@ -1102,9 +1160,14 @@ class Engine:
                 self._fork(lambda: _abi.check(self.lib.dmvae_step_tick(self.ctx, opt.state_dev.data_ptr(), opt.lr,
                                                                         opt.beta1, opt.beta2, self._stream())))
                 self._dp_opt = (opt, True) if mode == "all" else None
+                if self.stream_adam and self.dp is None and mode == "all" and self.timers is None and self.overlap:
+                    self._adam_live = (opt, [])
                 self.forward_backward(X, rows, None, None, kl_ratio, inv, off, recon_scale, True, mode, dev_state=opt)
                 self._dp_opt = None
-                self._update(opt, use_dev=True)
+                if self._adam_live is not None:
+                    self._adam_rest(opt)
+                else:
+                    self._update(opt, use_dev=True)
             n_nodes = int(self.lib.dmvae_ctx_launch_count(self.ctx)) - l0
             self._graphs[key] = (g, n_nodes)
             self._grads_dirty = False

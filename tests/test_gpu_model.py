@@ -199,6 +199,36 @@ def test_graph_replay_equals_eager_steps():
     assert res[1][2] >= res[0][2]          # replayed graph nodes are counted as launches
 
 
+@pytest.mark.parametrize("model,tier", [("dmvae", "bf16"), ("dmvae", "fp32"), ("vade", "bf16")])
+def test_streamed_adam_is_bit_identical(model, tier):
+    """Updating each layer block as soon as its gradient is final (side stream, beside the remaining gradient GEMMs)
+    must give exactly the parameters, Adam slots and losses of the single update at the end of the step."""
+    from dmvae_b200.engine import Engine
+    X, _, _ = _data(256, 784, 10, 10)
+    Xd = torch.tensor(X, device="cuda")
+    res = []
+    for streamed in (False, True):
+        cfg, eng, V = _make(model, tier)
+        eng.stream_adam = streamed
+        # split-K partial sums reduce in arrival order (cp.reduce.async.bulk): switch them off so that the bf16 tier is
+        # deterministic and the comparison can be exact
+        eng.split_k_wgrad = 1
+        eng._head_split_k = lambda rows: 1
+        opt = eng.optimizer("train", 0.002)
+        losses = []
+        for i in range(4):
+            eng.train_step(Xd, 256, opt)
+            losses.append(eng.loss_out.clone())
+        torch.cuda.synchronize()
+        res.append((torch.stack(losses).cpu(), eng.params.clone().cpu(), opt.m.clone().cpu(), opt.v.clone().cpu(),
+                    eng.grads.clone().cpu(), eng.launches()))
+        eng.close()
+    for nm, a, b in zip(("losses", "params", "m", "v", "grads"), res[0][:5], res[1][:5]):
+        assert torch.equal(a, b), (nm, float((a - b).abs().max()))
+    assert float(res[1][4].abs().max()) == 0.0                     # every block's gradient was cleared
+    assert res[1][5] > res[0][5]                                   # the streamed step has more (smaller) update launches
+
+
 def test_reference_api_training_reduces_loss():
     import dmvae_b200 as dm
     from dmvae_b200 import base_models, nn
