@@ -167,62 +167,100 @@ extern "C" int dmvae_stage_input(dmvae_ctx* ctx, const void* X, int x_dtype, int
 // Adam, TensorFlow semantics: theta -= lr_t * m / (sqrt(v) + eps)
 // 16 B read (p,g,m,v) + 12 B written (p,m,v) per parameter (+2 B bf16 copy, +4 B gradient clear).
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void adam_update1(float& p, float g, float& m, float& v, float lr_t, float b1, float b2,
+                                             float eps, float gs) {
+  const float gi = g * gs;
+  m = b1 * m + (1.f - b1) * gi;
+  v = b2 * v + (1.f - b2) * gi * gi;
+  p -= lr_t * m / (sqrtf(v) + eps);
+}
+
 __device__ __forceinline__ void adam_update4(float4& p, const float4 g, float4& m, float4& v, float lr_t, float b1,
                                              float b2, float eps, float gs) {
-  float* pp = &p.x;
-  float* mm = &m.x;
-  float* vv = &v.x;
-  const float* gg = &g.x;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    float gi = gg[i] * gs;
-    mm[i] = b1 * mm[i] + (1.f - b1) * gi;
-    vv[i] = b2 * vv[i] + (1.f - b2) * gi * gi;
-    pp[i] -= lr_t * mm[i] / (sqrtf(vv[i]) + eps);
+  adam_update1(p.x, g.x, m.x, v.x, lr_t, b1, b2, eps, gs);
+  adam_update1(p.y, g.y, m.y, v.y, lr_t, b1, b2, eps, gs);
+  adam_update1(p.z, g.z, m.z, v.z, lr_t, b1, b2, eps, gs);
+  adam_update1(p.w, g.w, m.w, v.w, lr_t, b1, b2, eps, gs);
+}
+
+__device__ __forceinline__ void adam_item(float* __restrict__ params, float* __restrict__ grads, float* __restrict__ m,
+                                          float* __restrict__ v, __nv_bfloat16* __restrict__ pbf, int64_t i, float lr_t,
+                                          float b1, float b2, float eps, float gs, int zero_grads, float4 p, float4 g,
+                                          float4 mm, float4 vv) {
+  adam_update4(p, g, mm, vv, lr_t, b1, b2, eps, gs);
+  reinterpret_cast<float4*>(params)[i] = p;
+  reinterpret_cast<float4*>(m)[i] = mm;
+  reinterpret_cast<float4*>(v)[i] = vv;
+  if (zero_grads) reinterpret_cast<float4*>(grads)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (pbf) {
+    __nv_bfloat162 lo = __floats2bfloat162_rn(p.x, p.y), hi = __floats2bfloat162_rn(p.z, p.w);
+    uint2 w = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+    reinterpret_cast<uint2*>(pbf)[i] = w;
   }
 }
 
-__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ params, float* __restrict__ grads,
-                                                    float* __restrict__ m, float* __restrict__ v,
-                                                    __nv_bfloat16* __restrict__ pbf, int64_t n4, float lr_t,
-                                                    const float* __restrict__ lr_t_dev, float b1, float b2, float eps,
-                                                    float gs, int zero_grads) {
+__global__ void __launch_bounds__(256, 6) adam_kernel(float* __restrict__ params, float* __restrict__ grads,
+                                                       float* __restrict__ m, float* __restrict__ v,
+                                                       __nv_bfloat16* __restrict__ pbf, int64_t n4, float lr_t,
+                                                       const float* __restrict__ lr_t_dev, float b1, float b2, float eps,
+                                                       float gs, int zero_grads) {
   pdl_wait();
   pdl_launch_dependents();
   if (lr_t_dev) lr_t = __ldg(lr_t_dev);
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (; i < n4; i += stride) {
-    float4 p = reinterpret_cast<float4*>(params)[i];
-    float4 g = reinterpret_cast<float4*>(grads)[i];
-    float4 mm = reinterpret_cast<float4*>(m)[i];
-    float4 vv = reinterpret_cast<float4*>(v)[i];
-    adam_update4(p, g, mm, vv, lr_t, b1, b2, eps, gs);
-    reinterpret_cast<float4*>(params)[i] = p;
-    reinterpret_cast<float4*>(m)[i] = mm;
-    reinterpret_cast<float4*>(v)[i] = vv;
-    if (zero_grads) reinterpret_cast<float4*>(grads)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (pbf) {
-      __nv_bfloat162 lo = __floats2bfloat162_rn(p.x, p.y), hi = __floats2bfloat162_rn(p.z, p.w);
-      uint2 w = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
-      reinterpret_cast<uint2*>(pbf)[i] = w;
-    }
+    const float4 p = reinterpret_cast<float4*>(params)[i];
+    const float4 g = reinterpret_cast<float4*>(grads)[i];
+    const float4 mm = reinterpret_cast<float4*>(m)[i];
+    const float4 vv = reinterpret_cast<float4*>(v)[i];
+    adam_item(params, grads, m, v, pbf, i, lr_t, b1, b2, eps, gs, zero_grads, p, g, mm, vv);
+  }
+}
+
+// Background shape of the same update (DMVAE_ADAM_BACKGROUND): 4-warp blocks.  The tcgen05 GEMM CTAs (10 warps x 152
+// registers: 3 warps on two of the SM's four register files) leave room for exactly one 40-register warp per scheduler,
+// so one such block per SM runs BESIDE a GEMM kernel instead of waiting for its CTAs to exit (a 256-thread block needs
+// two warps per scheduler and does not fit); when the GEMM CTAs do exit, up to 16 blocks per SM take over.
+__global__ void __launch_bounds__(128, 8) adam_bg_kernel(float* __restrict__ params, float* __restrict__ grads,
+                                                          float* __restrict__ m, float* __restrict__ v,
+                                                          __nv_bfloat16* __restrict__ pbf, int64_t n4, float lr_t,
+                                                          const float* __restrict__ lr_t_dev, float b1, float b2, float eps,
+                                                          float gs, int zero_grads) {
+  pdl_wait();
+  pdl_launch_dependents();
+  if (lr_t_dev) lr_t = __ldg(lr_t_dev);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 p = reinterpret_cast<float4*>(params)[i];
+    const float4 g = reinterpret_cast<float4*>(grads)[i];
+    const float4 mm = reinterpret_cast<float4*>(m)[i];
+    const float4 vv = reinterpret_cast<float4*>(v)[i];
+    adam_item(params, grads, m, v, pbf, i, lr_t, b1, b2, eps, gs, zero_grads, p, g, mm, vv);
   }
 }
 
 extern "C" int dmvae_adam(dmvae_ctx* ctx, float* params, float* grads, float* m, float* v, void* params_bf16, int64_t n,
                           float lr_t, const float* lr_t_dev, float beta1, float beta2, float eps, float grad_scale,
-                          int zero_grads, void* stream) {
+                          int flags, void* stream) {
   DMVAE_CHECK_ARG(ctx && params && grads && m && v, "dmvae_adam: NULL pointer");
   DMVAE_CHECK_ARG(n >= 0 && n % 4 == 0, "dmvae_adam: n (%lld) must be a multiple of 4 (flat padded buffer)", (long long)n);
   DMVAE_CHECK_ARG((((uintptr_t)params | (uintptr_t)grads | (uintptr_t)m | (uintptr_t)v) & 15) == 0 &&
                       ((uintptr_t)params_bf16 & 7) == 0,
                   "dmvae_adam: buffers must be 16-byte aligned");
+  DMVAE_CHECK_ARG((flags & ~(DMVAE_ADAM_ZERO_GRADS | DMVAE_ADAM_BACKGROUND)) == 0, "dmvae_adam: unknown flags %d", flags);
   if (n == 0) return DMVAE_OK;
+  const int zero_grads = flags & DMVAE_ADAM_ZERO_GRADS;
   int64_t n4 = n / 4;
-  int blocks = (int)min((int64_t)ctx->sm_count * 8, (n4 + 255) / 256);
-  dmvae_launch(adam_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, true, params, grads, m, v, (__nv_bfloat16*)params_bf16, n4, lr_t,
-                                                         lr_t_dev, beta1, beta2, eps, grad_scale, zero_grads);
+  if (flags & DMVAE_ADAM_BACKGROUND) {
+    int blocks = (int)min((int64_t)ctx->sm_count * 16, (n4 + 127) / 128);
+    dmvae_launch(adam_bg_kernel, dim3(blocks), dim3(128), 0, (cudaStream_t)stream, true, params, grads, m, v,
+                 (__nv_bfloat16*)params_bf16, n4, lr_t, lr_t_dev, beta1, beta2, eps, grad_scale, zero_grads);
+  } else {
+    int blocks = (int)min((int64_t)ctx->sm_count * 8, (n4 + 255) / 256);
+    dmvae_launch(adam_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, true, params, grads, m, v,
+                 (__nv_bfloat16*)params_bf16, n4, lr_t, lr_t_dev, beta1, beta2, eps, grad_scale, zero_grads);
+  }
   DMVAE_LAUNCH_CHECK(ctx);
   return DMVAE_OK;
 }

@@ -1042,9 +1042,21 @@ int launch_elbo_rowtile(dmvae_ctx* ctx, const ElboParams& p, cudaStream_t st) {
   constexpr bool kHasPrecise = sizeof(TD) == 2 && INPUT == DMVAE_INPUT_BINARY;
   auto kern = elbo_rowtile_kernel<TX, TD, INPUT, false>;
   if (kHasPrecise && precise) kern = elbo_rowtile_kernel<TX, TD, INPUT, kHasPrecise>;
-  if (smem > 48 * 1024) DMVAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int blocks = (p.a.rows + kFastRows - 1) / kFastRows;
-  dmvae_launch(kern, dim3(blocks), dim3(kFastThreads), smem, st, true, p);
+  // Small grids: the kernel is launched programmatically while its predecessor (a GEMM holding ~200 KB of shared memory
+  // on most SMs) still runs, and the CTA scheduler would pack the first CTAs four deep onto the few idle SMs.  Asking
+  // for proportionally more shared memory caps the CTAs per SM at the grid's own average depth, so the tile work
+  // spreads evenly once the predecessor's SMs free up.
+  size_t smem_req = smem;
+  const int depth = (blocks + ctx->sm_count - 1) / ctx->sm_count;
+  static int balance = -1;                    // DMVAE_ELBO_BALANCE=0: plain occupancy (A/B measurements)
+  if (balance < 0) {
+    const char* e = getenv("DMVAE_ELBO_BALANCE");
+    balance = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (balance && depth < 4) smem_req = max(smem, (size_t)(227 * 1024) / (size_t)(depth + 1) + 1024);
+  if (smem_req > 48 * 1024) DMVAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_req));
+  dmvae_launch(kern, dim3(blocks), dim3(kFastThreads), smem_req, st, true, p);
   DMVAE_LAUNCH_CHECK(ctx);
   return DMVAE_OK;
 }

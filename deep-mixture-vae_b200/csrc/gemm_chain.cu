@@ -75,7 +75,9 @@ __device__ __forceinline__ void decode_unit(const ChainParams& P, int u, int& e,
   out.kb1 = min(Ly.nkb, out.kb0 + Ly.kb_per_split);
 }
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
+// 160 registers (not the 168 ptxas would take): 10 warps x 160 leave room on the SM for one 256-thread block of the
+// streamed Adam update, which then runs BESIDE the grouped gradient GEMMs instead of waiting for their CTAs to exit
+__global__ void __cluster_dims__(2, 1, 1) __maxnreg__(152)
 gemm_chain_kernel(const __grid_constant__ ChainParams P) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2 * CH_STAGES + 4];

@@ -941,12 +941,12 @@ class Engine:
     stream_adam = os.environ.get("DMVAE_STREAM_ADAM", "1") != "0"
     _adam_live = None              # (AdamState, [(offset, n) already updated]) while a captured step streams its update
 
-    def _adam_range(self, opt: AdamState, off: int, n: int):
+    def _adam_range(self, opt: AdamState, off: int, n: int, background: bool = False):
         _abi.check(self.lib.dmvae_adam(self.ctx, self.params.data_ptr() + 4 * off, self.grads.data_ptr() + 4 * off,
                                        opt.m.data_ptr() + 4 * off, opt.v.data_ptr() + 4 * off,
                                        (self.params_op.data_ptr() + 2 * off) if self.params_op is not None else None,
-                                       n, 0.0, opt.state_dev.data_ptr() + 12, opt.beta1, opt.beta2, opt.eps, 1.0, 1,
-                                       self._stream()))
+                                       n, 0.0, opt.state_dev.data_ptr() + 12, opt.beta1, opt.beta2, opt.eps, 1.0,
+                                       3 if background else 1, self._stream()))
 
     def _block_range(self, name: str) -> Tuple[int, int]:
         if name == "priors":
@@ -968,7 +968,7 @@ class Engine:
 
         def run():
             for off, n in merged:
-                self._adam_range(opt, off, n)
+                self._adam_range(opt, off, n, background=self.dt == BF16)
 
         self._fork(run)
         done.extend(merged)

@@ -234,9 +234,11 @@ int dmvae_stage_features(dmvae_ctx* ctx, const float* src, int64_t ld, int rows,
 /* ---- TF-semantics Adam (tf.train.AdamOptimizer, base_models.py:102-110) ---------------------
  * theta -= lr_t m/(sqrt(v)+eps), lr_t = lr sqrt(1-b2^t)/(1-b1^t) computed by the caller in double.
  * Flat over n fp32 parameters.  Optionally writes the bf16 operand copy and clears the gradient. */
+#define DMVAE_ADAM_ZERO_GRADS 1 /* clear the gradient after the update */
+#define DMVAE_ADAM_BACKGROUND 2 /* small-block launch shape that co-resides with a running GEMM kernel (streamed update) */
 int dmvae_adam(dmvae_ctx* ctx, float* params, float* grads, float* m, float* v, void* params_bf16 /* or NULL */,
                int64_t n, float lr_t, const float* lr_t_dev /* optional device scalar overriding lr_t */,
-               float beta1, float beta2, float eps, float grad_scale, int zero_grads, void* stream);
+               float beta1, float beta2, float eps, float grad_scale, int flags /* DMVAE_ADAM_* */, void* stream);
 /* Per-step device state for CUDA-graph replay: state = {uint64 step; uint32 t; float lr_t}.  One tiny kernel:
  * step += 1, t += 1, lr_t = lr sqrt(1-beta2^t)/(1-beta1^t) (double precision). */
 int dmvae_step_tick(dmvae_ctx* ctx, void* state_dev, float lr, float beta1, float beta2, void* stream);
