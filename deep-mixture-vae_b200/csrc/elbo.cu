@@ -428,11 +428,13 @@ struct Tile8<uint8_t> {
 };
 
 // =================================================================================================
-// Row-tile kernel for the common small-mixture case (DMVAE analytic KL, K*L small): a CTA owns 32 rows.
-//   warps 0-7 : stream the D-wide reconstruction part, 4 rows per warp treated as ONE list of 8-element chunks
-//               (no per-row tail iteration); every chunk's loads are issued before the first is consumed.
-//   warp  8   : the latent part with lane <-> row (K*L is tiny: one thread walks it serially, so the 32 rows
-//               cost ~K*L warp-instructions instead of ~32 x (shuffles + shared-memory round trips) per row).
+// Row-tile kernel for the common small-mixture case (DMVAE analytic KL, K*L small): a CTA owns 16 rows, 4 CTAs per SM.
+//   warps 0-7 : stream the D-wide reconstruction part from a shared-memory tile (one bulk async copy per tensor in,
+//               one out), 2 rows per warp treated as ONE list of 8-element chunks (no per-row tail iteration);
+//               fp32, one MUFU (tanh) per element in the bf16 tier (recon8_t).
+//   warps 8-9 : the latent part, 8 rows per warp and four lanes per row; for L <= 16 a register-resident single sweep
+//               over the K components (rowtile_latent), else the generic two-pass loops.  They run beside the
+//               streaming warps and only meet them at one named barrier (the row's reconstruction sum).
 // Same formulas and outputs as elbo_kernel.
 // =================================================================================================
 constexpr int kFastRW = 2;                  // rows per reconstruction warp
@@ -1043,20 +1045,8 @@ int launch_elbo_rowtile(dmvae_ctx* ctx, const ElboParams& p, cudaStream_t st) {
   auto kern = elbo_rowtile_kernel<TX, TD, INPUT, false>;
   if (kHasPrecise && precise) kern = elbo_rowtile_kernel<TX, TD, INPUT, kHasPrecise>;
   const int blocks = (p.a.rows + kFastRows - 1) / kFastRows;
-  // Small grids: the kernel is launched programmatically while its predecessor (a GEMM holding ~200 KB of shared memory
-  // on most SMs) still runs, and the CTA scheduler would pack the first CTAs four deep onto the few idle SMs.  Asking
-  // for proportionally more shared memory caps the CTAs per SM at the grid's own average depth, so the tile work
-  // spreads evenly once the predecessor's SMs free up.
-  size_t smem_req = smem;
-  const int depth = (blocks + ctx->sm_count - 1) / ctx->sm_count;
-  static int balance = -1;                    // DMVAE_ELBO_BALANCE=0: plain occupancy (A/B measurements)
-  if (balance < 0) {
-    const char* e = getenv("DMVAE_ELBO_BALANCE");
-    balance = (e && e[0] == '0') ? 0 : 1;
-  }
-  if (balance && depth < 4) smem_req = max(smem, (size_t)(227 * 1024) / (size_t)(depth + 1) + 1024);
-  if (smem_req > 48 * 1024) DMVAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_req));
-  dmvae_launch(kern, dim3(blocks), dim3(kFastThreads), smem_req, st, true, p);
+  if (smem > 48 * 1024) DMVAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dmvae_launch(kern, dim3(blocks), dim3(kFastThreads), smem, st, true, p);
   DMVAE_LAUNCH_CHECK(ctx);
   return DMVAE_OK;
 }
