@@ -473,6 +473,22 @@ class Engine:
                                              self._stream()))
         self._toc("gemm", t0)
 
+    group_heads = os.environ.get("DMVAE_HEAD_GROUP", "1") != "0"
+    head_group_split = int(os.environ.get("DMVAE_HEAD_GROUP_SPLIT", "2"))
+
+    def _fwd_entry(self, name, A, lda, Y, rows, split_k):
+        """Grouped-launch entry of a linear layer whose k-splits reduce into the cleared fp32 output Y."""
+        ly = self.layers[name]
+        g = _abi.ChainGemm()                     # Y[rows, out_pad] += A[rows, in_pad] . W[in_pad, out_pad]
+        g.trans_a, g.trans_b = 0, 0
+        g.A, g.lda, g.B, g.ldb = A.data_ptr(), lda, self.W(name, op=True).data_ptr(), ly.out_pad
+        g.C, g.ldc = Y.data_ptr(), Y.stride(0)
+        g.M, g.N, g.K = rows, ly.out_pad, ly.in_pad
+        g.epi.out_dtype, g.epi.act, g.epi.n_valid, g.epi.n_block, g.epi.pad_one = F32, _abi.ACT_NONE, 1 << 30, 1 << 30, 0.0
+        g.epi.accumulate, g.epi.split_k = 1, split_k
+        g.dep[0], g.dep[1] = -1, -1
+        return g
+
     # ---- grouped backward: the weight-gradient and data-gradient GEMMs that become runnable together go out as ONE
     #      persistent launch (dmvae_gemm_chain without dependencies) instead of one launch each on two streams: the
     #      separate launches could not overlap anyway (each CTA pair takes a whole SM pair's shared memory), and every
@@ -634,6 +650,15 @@ class Engine:
             h = self.act["ench"]
             if sk > 1:
                 self._join()
+            if "c" in heads and "z" in heads and sk > 1 and self.group_heads and self.use_groups and self.timers is None:
+                # both heads as ONE grouped launch of the CTA-pair kernel: 2 heads x 16 row blocks x k-splits work units in
+                # a single wave over the 74 SM pairs (the two single-CTA launches on two streams took two waves: each of
+                # their CTAs holds a whole SM's shared memory)
+                gs = self.head_group_split
+                arr = (_abi.ChainGemm * 2)(self._fwd_entry("zh", h, h.stride(0), self.zh, rows, gs),
+                                           self._fwd_entry("ch", h[:, hp:], h.stride(0), self.ch, rows, gs))
+                _abi.check(self.lib.dmvae_gemm_chain(self.ctx, arr, 2, None, 0, 0, None, self._stream()))
+                return
             if "c" in heads:
                 if "z" in heads:
                     self._fork(lambda: self._fwd("ch", h[:, hp:], h.stride(0), self.ch, F32, _abi.ACT_NONE, rows, split_k=sk))
