@@ -76,8 +76,9 @@ extern "C" int dmvae_zero_f32(dmvae_ctx* ctx, float* p, int64_t n, void* stream)
   DMVAE_CHECK_ARG(((uintptr_t)p & 15) == 0, "dmvae_zero_f32: pointer must be 16-byte aligned");
   if (n == 0) return DMVAE_OK;
   int64_t n4 = n / 4;
-  int blocks = (int)min((int64_t)ctx->sm_count * 8, (n4 + 255) / 256 + 1);
-  dmvae_launch(zero_f32_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, true, (float4*)p, p + n4 * 4, n4, n - n4 * 4);
+  // 4-warp blocks: they fit beside the tcgen05 GEMM CTAs (one free warp slot per scheduler), see adam_bg_kernel
+  int blocks = (int)min((int64_t)ctx->sm_count * 16, (n4 + 127) / 128 + 1);
+  dmvae_launch(zero_f32_kernel, dim3(blocks), dim3(128), 0, (cudaStream_t)stream, true, (float4*)p, p + n4 * 4, n4, n - n4 * 4);
   DMVAE_LAUNCH_CHECK(ctx);
   return DMVAE_OK;
 }
@@ -337,7 +338,7 @@ __global__ void __launch_bounds__(256) dp_reduce_adam_kernel(DpPeers peers, int 
 extern "C" int dmvae_dp_reduce_adam(dmvae_ctx* ctx, int rank, int world, float* const* grads_peers_host,
                                     float* const* params_peers_host, void* const* params_bf16_peers_host, float* m,
                                     float* v, int64_t n, int64_t shard_begin, int64_t shard_end, float lr_t,
-                                    const float* lr_t_dev, float beta1, float beta2, float eps, int clear_grads,
+                                    const float* lr_t_dev, float beta1, float beta2, float eps, int flags,
                                     void* stream) {
   DMVAE_CHECK_ARG(ctx && grads_peers_host && params_peers_host && m && v, "dmvae_dp_reduce_adam: NULL pointer");
   DMVAE_CHECK_ARG(world >= 1 && world <= 8 && rank >= 0 && rank < world, "dmvae_dp_reduce_adam: world %d rank %d", world, rank);
@@ -354,10 +355,14 @@ extern "C" int dmvae_dp_reduce_adam(dmvae_ctx* ctx, int rank, int world, float* 
                     "dmvae_dp_reduce_adam: peer %d: gradient pointer, and fp32 or bf16 parameter pointer, required", r);
   }
   if (shard_end == shard_begin) return DMVAE_OK;
+  DMVAE_CHECK_ARG((flags & ~(DMVAE_ADAM_ZERO_GRADS | DMVAE_ADAM_BACKGROUND)) == 0, "dmvae_dp_reduce_adam: unknown flags %d", flags);
   int64_t n4 = (shard_end - shard_begin) / 4;
-  int blocks = (int)min((int64_t)ctx->sm_count * 8, (n4 + 255) / 256);
-  dp_reduce_adam_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(peers, rank, world, m, v, shard_begin / 4, shard_end / 4,
-                                                                   lr_t, lr_t_dev, beta1, beta2, eps, clear_grads);
+  // DMVAE_ADAM_BACKGROUND: 4-warp blocks that fit beside the GEMM CTAs (see adam_bg_kernel)
+  const int threads = (flags & DMVAE_ADAM_BACKGROUND) ? 128 : 256;
+  int blocks = (int)min((int64_t)ctx->sm_count * (2048 / threads), (n4 + threads - 1) / threads);
+  dp_reduce_adam_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(peers, rank, world, m, v, shard_begin / 4, shard_end / 4,
+                                                                       lr_t, lr_t_dev, beta1, beta2, eps,
+                                                                       flags & DMVAE_ADAM_ZERO_GRADS);
   DMVAE_LAUNCH_CHECK(ctx);
   return DMVAE_OK;
 }

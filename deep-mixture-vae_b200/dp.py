@@ -140,8 +140,21 @@ class DataParallel:
     # ---- ranges: the flat buffer is exchanged as encoder | decoder | tail (experts, prior tables).  The decoder's
     #      gradients are complete half way through the backward pass, so their exchange overlaps the encoder's
     #      backward GEMMs on a forked stream; the rest is exchanged at the end of the step. ----
+    # Streamed exchange (default in mode "p2p"): the engine's backward pass hands over each range of the flat buffer as
+    # soon as its gradients are final (Engine._adam_segment); barrier -> reduce + Adam on the owned shard -> barrier ->
+    # local gradient clear run on the side stream beside the remaining gradient GEMMs, in 4-warp blocks that fit next to
+    # the GEMM CTAs (see adam_bg_kernel).  Only the first encoder layer's range is left for the end of the step.
+    # Off by default: measured on 2 x B200 the four extra barrier pairs cost more than the overlap hides (0.368 vs
+    # 0.334 ms / step with every segment streamed); DMVAE_DP_STREAM=1 enables it.
+    stream = os.environ.get("DMVAE_DP_STREAM", "0") == "1"
+
+    def can_stream(self) -> bool:
+        return self.mode == "p2p" and self.stream and not self.overlap_decoder
+
     def ranges(self):
         eng = self.eng
+        if self.can_stream():
+            return eng.stream_partition()
         if not self.overlap_decoder:
             return [(0, eng.n_params)]
         dec0 = eng.layers[eng.dec_chain[0]].offset
@@ -164,7 +177,14 @@ class DataParallel:
                                      torch.zeros(n, dtype=torch.float32, device=self.eng.device))
         return self._opt_shards[key]
 
-    def _exchange(self, opt, lr_t, lr_dev, ridxs, ch):
+    def segment(self, opt, merged):
+        """Exchange + update of the partition ranges `merged` [(offset, n)] (captured steps: device-resident lr_t)."""
+        rs = self.ranges()
+        for off, n in merged:
+            ridx = rs.index((off, off + n))
+            self._exchange(opt, 0.0, opt.state_dev.data_ptr() + 12, [ridx], 2 + 2 * ridx, background=True)
+
+    def _exchange(self, opt, lr_t, lr_dev, ridxs, ch, background=False):
         eng, abi = self.eng, self._abi
         self.hdl.barrier(channel=ch)                      # every rank's gradients of these ranges are complete
         for ridx in ridxs:
@@ -174,7 +194,8 @@ class DataParallel:
             m, v = self._opt_shard_state(opt, ridx)
             abi.check(eng.lib.dmvae_dp_reduce_adam(eng.ctx, self.rank, self.world, self._g_ptrs, self._p_ptrs,
                                                    self._b_ptrs, m.data_ptr(), v.data_ptr(), eng.n_params, b, e, lr_t,
-                                                   lr_dev, opt.beta1, opt.beta2, opt.eps, 0, eng._stream()))
+                                                   lr_dev, opt.beta1, opt.beta2, opt.eps, 2 if background else 0,
+                                                   eng._stream()))
         self.hdl.barrier(channel=ch + 1)                  # every replica updated, every gradient shard consumed
         # clear the local gradients of these ranges (split-K accumulates into them): local HBM, not 7/8 remote stores
         for ridx in ridxs:
@@ -197,8 +218,17 @@ class DataParallel:
         self._early_done = True
 
     # ---- the exchange + update ---------------------------------------------------------------------------
-    def update(self, opt, use_dev: bool = False):
+    def update(self, opt, use_dev: bool = False, skip=None):
+        """skip: [(offset, n)] ranges already exchanged by segment() during this step."""
         eng, abi = self.eng, self._abi
+        if skip:
+            lr_dev = opt.state_dev.data_ptr() + 12
+            rs = self.ranges()
+            gone = set((off, off + n) for off, n in skip)
+            self._exchange(opt, 0.0, lr_dev, [i for i, r in enumerate(rs) if r not in gone], 0)
+            self._master_stale = self.master_sharded
+            eng._grads_dirty = False
+            return
         early = getattr(self, "_early_done", False)
         self._early_done = False
         if early:

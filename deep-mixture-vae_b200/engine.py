@@ -79,6 +79,52 @@ class Layout:
         self.off_log_vars = off + self.tab_size
         self.n_params = off + 2 * self.tab_size
 
+    def block_range(self, name: str) -> Tuple[int, int]:
+        """(offset, n) of a dense layer's block, or of the two prior tables ("priors")."""
+        if name == "priors":
+            return self.off_means, 2 * self.tab_size
+        ly = self.layers[name]
+        return ly.offset, ly.size
+
+    def stream_plan(self) -> Dict[str, List[str]]:
+        """Which blocks become final together during the backward pass (key -> block names), in the order they do."""
+        chain = self.dec_chain
+        plan: Dict[str, List[str]] = {}
+        top = ["decx", "priors"]
+        if len(chain) > 1:
+            plan["dec"] = list(chain[1:]) + top          # the decoder above its first layer (+ the prior tables)
+            top = []
+        plan["heads"] = (["zh", "ch"] if self.model == "dmvae" else ["zh"]) + [chain[0]] + top
+        if self.model == "dmvae":
+            plan["ench"] = ["ench"]
+        for nm in self.enc_chain[1:]:
+            plan["enc:" + nm] = [nm]
+        return plan
+
+    def merged_ranges(self, names) -> List[Tuple[int, int]]:
+        """(offset, n) of the blocks `names`, adjacent blocks merged."""
+        merged: List[Tuple[int, int]] = []
+        for off, n in sorted(self.block_range(nm) for nm in names):
+            if merged and merged[-1][0] + merged[-1][1] == off:
+                merged[-1] = (merged[-1][0], merged[-1][1] + n)
+            else:
+                merged.append((off, n))
+        return merged
+
+    def stream_partition(self) -> List[Tuple[int, int]]:
+        """[lo, hi) ranges tiling the flat buffer: one per streamed segment plus whatever lies between them (the first
+        encoder layer, expert blocks).  The data-parallel exchange shards each range separately."""
+        rs = sorted(r for names in self.stream_plan().values() for r in self.merged_ranges(names))
+        out, pos = [], 0
+        for lo, n in rs:
+            if lo > pos:
+                out.append((pos, lo))
+            out.append((lo, lo + n))
+            pos = lo + n
+        if pos < self.n_params:
+            out.append((pos, self.n_params))
+        return out
+
     def reference_parameter_count(self) -> int:
         """Number of reference parameters that receive a gradient (4 373 014 for cfg1/2)."""
         return int(sum(int(np.prod(v.shape)) for v in self.vars.values()))
@@ -859,7 +905,7 @@ class Engine:
                     self._dgrad(nm, dy, dy.stride(0), None, 0, self.dz, F32, rows, self.L, self.dz.shape[1], split_k=sk)
                 self._flush_group()
                 if i == 1:                           # the decoder above its first layer is final (+ the prior tables)
-                    self._adam_segment(chain[1:] + ["decx", "priors"])
+                    self._adam_segment("dec")
         # data parallel: the decoder's gradients are complete - exchange them while the encoder's backward runs
         dpo = getattr(self, "_dp_opt", None)
         if (self.dp is not None and dpo is not None and getattr(self.dp, "overlap_decoder", False) and through_decoder
@@ -888,7 +934,7 @@ class Engine:
                 self._wgrad("ch", h[:, hp:], h.stride(0), self.dch, self.dch.stride(0), rows)
                 self._dgrad("ch", self.dch, self.dch.stride(0), h[:, hp:], h.stride(0), dh[:, hp:], dt, rows, hv, hp)
             self._flush_group()                      # both heads' four GEMMs: one launch
-            self._adam_segment(["zh", "ch", chain[0]] + ([] if len(chain) > 1 else ["decx", "priors"]))
+            self._adam_segment("heads")
             a_in = self.act[self.enc_chain[-1]]
             if train_z and train_c:
                 self._wgrad("ench", a_in, a_in.stride(0), dh, dh.stride(0), rows)
@@ -907,7 +953,7 @@ class Engine:
                     self._dgrad("ench", dh[:, c0:], dh.stride(0), a_in, a_in.stride(0), self.dact[self.enc_chain[-1]], dt,
                                 rows, lp.n_valid, lp.n_block, W=Wsub, ldw=self.layers["ench"].out_pad, n_out_pad=hp)
             self._flush_group()
-            self._adam_segment(["ench"])
+            self._adam_segment("ench")
         else:
             if train_z:
                 a_in = self.act[self.enc_chain[-1]]
@@ -916,7 +962,7 @@ class Engine:
                 self._dgrad("zh", self.dzh, self.dzh.stride(0), a_in, a_in.stride(0), self.dact[self.enc_chain[-1]], dt,
                             rows, lp.n_valid, lp.n_block)
                 self._flush_group()
-                self._adam_segment(["zh", chain[0]] + ([] if len(chain) > 1 else ["decx", "priors"]))
+                self._adam_segment("heads")
         # ---- encoder trunk ----
         if train_trunk:
             ec = self.enc_chain
@@ -931,7 +977,7 @@ class Engine:
                                 lp.n_block)
                 self._flush_group()
                 if i > 0:
-                    self._adam_segment([nm])
+                    self._adam_segment("enc:" + nm)
         self._end_group()
         self._join()
 
@@ -974,24 +1020,34 @@ class Engine:
                                        3 if background else 1, self._stream()))
 
     def _block_range(self, name: str) -> Tuple[int, int]:
-        if name == "priors":
-            return self.layout.off_means, 2 * self.layout.tab_size
-        ly = self.layers[name]
-        return ly.offset, ly.size
+        return self.layout.block_range(name)
 
-    def _adam_segment(self, names):
-        """Blocks `names` are final: update them now on the side stream (contiguous blocks share one launch)."""
+    def _stream_plan(self) -> Dict[str, List[str]]:
+        return self.layout.stream_plan()
+
+    def _merged_ranges(self, names) -> List[Tuple[int, int]]:
+        return self.layout.merged_ranges(names)
+
+    def stream_partition(self) -> List[Tuple[int, int]]:
+        return self.layout.stream_partition()
+
+    def _adam_segment(self, key: str):
+        """The blocks of plan entry `key` are final: update them now on the side stream (contiguous blocks share one
+        launch; with data parallelism: exchange + update of that range)."""
         if self._adam_live is None:
             return
+        names = self._stream_plan().get(key)
+        if not names:
+            return
+        if self.dp is not None and key.startswith("enc:"):
+            return                                   # a separate exchange (two cross-GPU barriers) right before the final one only lengthens the tail
         opt, done = self._adam_live
-        merged = []
-        for off, n in sorted(self._block_range(nm) for nm in names):
-            if merged and merged[-1][0] + merged[-1][1] == off:
-                merged[-1] = (merged[-1][0], merged[-1][1] + n)
-            else:
-                merged.append((off, n))
+        merged = self._merged_ranges(names)
 
         def run():
+            if self.dp is not None:
+                self.dp.segment(opt, merged)
+                return
             for off, n in merged:
                 self._adam_range(opt, off, n, background=self.dt == BF16)
 
@@ -1002,6 +1058,9 @@ class Engine:
         """The blocks no segment covered (the tail of the step)."""
         done = sorted(self._adam_live[1])
         self._adam_live = None
+        if self.dp is not None:
+            self.dp.update(opt, True, skip=done)
+            return
         pos = 0
         for off, n in done + [(self.n_params, 0)]:
             if off > pos:
@@ -1185,7 +1244,8 @@ class Engine:
                 self._fork(lambda: _abi.check(self.lib.dmvae_step_tick(self.ctx, opt.state_dev.data_ptr(), opt.lr,
                                                                         opt.beta1, opt.beta2, self._stream())))
                 self._dp_opt = (opt, True) if mode == "all" else None
-                if self.stream_adam and self.dp is None and mode == "all" and self.timers is None and self.overlap:
+                if (self.stream_adam and mode == "all" and self.timers is None and self.overlap
+                        and (self.dp is None or self.dp.can_stream())):
                     self._adam_live = (opt, [])
                 self.forward_backward(X, rows, None, None, kl_ratio, inv, off, recon_scale, True, mode, dev_state=opt)
                 self._dp_opt = None

@@ -256,7 +256,8 @@ int dmvae_dp_reduce_adam(dmvae_ctx* ctx, int rank, int world, float* const* grad
                          float* const* params_peers_host, void* const* params_bf16_peers_host,
                          float* m, float* v, int64_t n, int64_t shard_begin, int64_t shard_end,
                          float lr_t, const float* lr_t_dev, float beta1, float beta2, float eps,
-                         int clear_grads /* 0: every rank clears its own gradient buffer after the closing barrier */,
+                         int flags /* DMVAE_ADAM_ZERO_GRADS: clear the consumed shard in every replica (0: every rank clears its
+                                      own gradient buffer after the closing barrier); DMVAE_ADAM_BACKGROUND: small blocks */,
                          void* stream);
 /* params_peers_host[r] may be NULL for r != rank when params_bf16_peers_host[r] is given: the fp32 master copy of a
  * shard then lives on its owner only (the bf16 operand copy, which is all the GEMMs read, is still replicated). */

@@ -38,21 +38,46 @@ def test_range_shards_partition_the_flat_buffer():
         pass
     lay = Layout(model="dmvae", input_dim=784, latent_dim=10, n_classes=10, trunk=(500, 500), head=2000,
                  decoder=(2000, 500, 500), name="dmvae")
-    for overlap in (False, True):
+    for overlap, stream in ((False, False), (True, False), (False, True)):
         for world in (1, 2, 4, 8):
             covered = np.zeros(lay.n_params, np.int32)
             for rank in range(world):
                 d = dp.DataParallel.__new__(dp.DataParallel)
                 eng = Stub()
                 eng.layers, eng.dec_chain, eng.n_params = lay.layers, lay.dec_chain, lay.n_params
-                d.eng, d.rank, d.world, d.overlap_decoder = eng, rank, world, overlap
+                eng.stream_partition = lay.stream_partition
+                d.eng, d.rank, d.world, d.overlap_decoder, d.mode, d.stream = eng, rank, world, overlap, "p2p", stream
                 rr = d.ranges()
-                assert rr[0][0] == 0 and rr[-1][1] == lay.n_params and len(rr) == (3 if overlap else 1)
+                # streamed: enc1 | enc2 | ench | zh ch dec1 | dec2 dec3 decx + prior tables
+                assert rr[0][0] == 0 and rr[-1][1] == lay.n_params and len(rr) == (5 if stream else 3 if overlap else 1)
+                assert all(rr[i][1] == rr[i + 1][0] for i in range(len(rr) - 1))
                 for i in range(len(rr)):
                     b, e = d.range_shard(i)
                     assert b % 4 == 0 and e % 4 == 0 and rr[i][0] <= b <= e <= rr[i][1]
                     covered[b:e] += 1
             assert (covered == 1).all()
+
+
+def test_stream_plan_covers_every_block_once():
+    """Layout.stream_plan / stream_partition (host logic of the streamed update): every block is in at most one
+    segment, segments are contiguous ranges, and only the first encoder layer is left for the end of the step."""
+    from dmvae_b200.engine import Layout
+    for kw in (dict(model="dmvae", trunk=(500, 500), head=2000, decoder=(2000, 500, 500)),
+               dict(model="vade", trunk=(2000, 500, 500), head=0, decoder=(500, 500, 2000)),
+               dict(model="dmvae", trunk=(500, 500), head=2000, decoder=(2000,))):
+        lay = Layout(input_dim=784, latent_dim=10, n_classes=10, name="m", **kw)
+        plan = lay.stream_plan()
+        names = [n for v in plan.values() for n in v]
+        assert len(names) == len(set(names))
+        assert set(names) == (set(lay.layers) | {"priors"}) - {lay.enc_chain[0]}
+        part = lay.stream_partition()
+        assert part[0][0] == 0 and part[-1][1] == lay.n_params
+        assert all(part[i][1] == part[i + 1][0] for i in range(len(part) - 1))
+        for v in plan.values():
+            for off, n in lay.merged_ranges(v):
+                assert (off, off + n) in part
+        e1 = lay.layers[lay.enc_chain[0]]
+        assert (e1.offset, e1.offset + e1.size) in part
 
 
 def _free_port():
