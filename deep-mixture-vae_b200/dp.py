@@ -144,12 +144,15 @@ class DataParallel:
     # soon as its gradients are final (Engine._adam_segment); barrier -> reduce + Adam on the owned shard -> barrier ->
     # local gradient clear run on the side stream beside the remaining gradient GEMMs, in 4-warp blocks that fit next to
     # the GEMM CTAs (see adam_bg_kernel).  Only the first encoder layer's range is left for the end of the step.
-    # Off by default: measured on 2 x B200 the four extra barrier pairs cost more than the overlap hides (0.368 vs
-    # 0.334 ms / step with every segment streamed); DMVAE_DP_STREAM=1 enables it.
+    # EXPERIMENTAL, off by default: measured on 2 x B200 the extra cross-GPU barrier pairs cost more than the overlap
+    # hides (0.357 ms / step with the three large segments streamed, 0.368 with all four, against 0.334 for the single
+    # exchange), and scripts/dp_check.py's fp32 + CUDA-graph configuration did not terminate with it.
+    # DMVAE_DP_STREAM=1 enables it (bf16 tier).
     stream = os.environ.get("DMVAE_DP_STREAM", "0") == "1"
 
     def can_stream(self) -> bool:
-        return self.mode == "p2p" and self.stream and not self.overlap_decoder
+        return (self.mode == "p2p" and self.stream and not self.overlap_decoder
+                and getattr(self.eng, "params_op", None) is not None)
 
     def ranges(self):
         eng = self.eng

@@ -45,7 +45,7 @@ def test_range_shards_partition_the_flat_buffer():
                 d = dp.DataParallel.__new__(dp.DataParallel)
                 eng = Stub()
                 eng.layers, eng.dec_chain, eng.n_params = lay.layers, lay.dec_chain, lay.n_params
-                eng.stream_partition = lay.stream_partition
+                eng.stream_partition, eng.params_op = lay.stream_partition, object()
                 d.eng, d.rank, d.world, d.overlap_decoder, d.mode, d.stream = eng, rank, world, overlap, "p2p", stream
                 rr = d.ranges()
                 # streamed: enc1 | enc2 | ench | zh ch dec1 | dec2 dec3 decx + prior tables
