@@ -300,19 +300,33 @@ struct DpPeers {
   __nv_bfloat16* pbf[8];
 };
 
-__global__ void __launch_bounds__(256) dp_reduce_adam_kernel(DpPeers peers, int rank, int world, float* __restrict__ m,
+// WORLD > 0: compile-time rank count - the peer loads are unrolled and ALL issued before the first add (a run-time loop
+// waits out one NVLink round trip per peer, ~2 us each); WORLD == 0: generic.
+template <int WORLD>
+__global__ void __launch_bounds__(256) dp_reduce_adam_kernel(DpPeers peers, int rank, int world_rt, float* __restrict__ m,
                                                               float* __restrict__ v, int64_t begin4, int64_t end4,
                                                               float lr_t, const float* __restrict__ lr_t_dev, float b1,
                                                               float b2, float eps, int clear_grads) {
+  const int world = WORLD > 0 ? WORLD : world_rt;
   if (lr_t_dev) lr_t = __ldg(lr_t_dev);
   int64_t i = begin4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (; i < end4; i += stride) {
     // fixed summation order (rank 0 .. world-1) so that every step is reproducible
-    float4 g = reinterpret_cast<const float4*>(peers.grads[0])[i];
-    for (int r = 1; r < world; ++r) {
-      float4 t = reinterpret_cast<const float4*>(peers.grads[r])[i];
-      g.x += t.x; g.y += t.y; g.z += t.z; g.w += t.w;
+    float4 g;
+    if (WORLD > 0) {
+      float4 t[WORLD > 0 ? WORLD : 1];
+#pragma unroll
+      for (int r = 0; r < WORLD; ++r) t[r] = reinterpret_cast<const float4*>(peers.grads[r])[i];
+      g = t[0];
+#pragma unroll
+      for (int r = 1; r < WORLD; ++r) { g.x += t[r].x; g.y += t[r].y; g.z += t[r].z; g.w += t[r].w; }
+    } else {
+      g = reinterpret_cast<const float4*>(peers.grads[0])[i];
+      for (int r = 1; r < world; ++r) {
+        float4 t = reinterpret_cast<const float4*>(peers.grads[r])[i];
+        g.x += t.x; g.y += t.y; g.z += t.z; g.w += t.w;
+      }
     }
     // this rank is the only reader of element i of every replica's gradient: clear it for the next step's
     // split-K accumulation (or leave that to a local pass of each rank after the closing barrier: 7/8 of these
@@ -360,9 +374,12 @@ extern "C" int dmvae_dp_reduce_adam(dmvae_ctx* ctx, int rank, int world, float* 
   // DMVAE_ADAM_BACKGROUND: 4-warp blocks that fit beside the GEMM CTAs (see adam_bg_kernel)
   const int threads = (flags & DMVAE_ADAM_BACKGROUND) ? 128 : 256;
   int blocks = (int)min((int64_t)ctx->sm_count * (2048 / threads), (n4 + threads - 1) / threads);
-  dp_reduce_adam_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(peers, rank, world, m, v, shard_begin / 4, shard_end / 4,
-                                                                       lr_t, lr_t_dev, beta1, beta2, eps,
-                                                                       flags & DMVAE_ADAM_ZERO_GRADS);
+  auto kern = dp_reduce_adam_kernel<0>;
+  if (world == 2) kern = dp_reduce_adam_kernel<2>;
+  else if (world == 4) kern = dp_reduce_adam_kernel<4>;
+  else if (world == 8) kern = dp_reduce_adam_kernel<8>;
+  kern<<<blocks, threads, 0, (cudaStream_t)stream>>>(peers, rank, world, m, v, shard_begin / 4, shard_end / 4, lr_t, lr_t_dev,
+                                                     beta1, beta2, eps, flags & DMVAE_ADAM_ZERO_GRADS);
   DMVAE_LAUNCH_CHECK(ctx);
   return DMVAE_OK;
 }

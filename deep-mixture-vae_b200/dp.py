@@ -187,6 +187,10 @@ class DataParallel:
             ridx = rs.index((off, off + n))
             self._exchange(opt, 0.0, opt.state_dev.data_ptr() + 12, [ridx], 2 + 2 * ridx, background=True)
 
+    # Captured steps leave the consumed gradients in place and clear them at the START of the next replay, on the forked
+    # stream beside the forward pass (Engine._train_step_graph), instead of as the last kernel of the step.
+    defer_clear = False
+
     def _exchange(self, opt, lr_t, lr_dev, ridxs, ch, background=False):
         eng, abi = self.eng, self._abi
         self.hdl.barrier(channel=ch)                      # every rank's gradients of these ranges are complete
@@ -201,6 +205,8 @@ class DataParallel:
                                                    eng._stream()))
         self.hdl.barrier(channel=ch + 1)                  # every replica updated, every gradient shard consumed
         # clear the local gradients of these ranges (split-K accumulates into them): local HBM, not 7/8 remote stores
+        if self.defer_clear:
+            return
         for ridx in ridxs:
             lo, hi = self.ranges()[ridx]
             if hi > lo:

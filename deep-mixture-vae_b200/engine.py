@@ -1243,6 +1243,13 @@ class Engine:
                 # the side stream, off the head of the critical path
                 self._fork(lambda: _abi.check(self.lib.dmvae_step_tick(self.ctx, opt.state_dev.data_ptr(), opt.lr,
                                                                         opt.beta1, opt.beta2, self._stream())))
+                # data parallel (peer-memory exchange): the gradients consumed by the previous step's exchange are cleared
+                # here, beside the forward pass, rather than as the last kernel of that step
+                defer = self.dp is not None and getattr(self.dp, "mode", "") == "p2p" and mode == "all"
+                if defer:
+                    self._fork(lambda: _abi.check(self.lib.dmvae_zero_f32(self.ctx, self.grads.data_ptr(), self.n_params,
+                                                                          self._stream())))
+                    self.dp.defer_clear = True
                 self._dp_opt = (opt, True) if mode == "all" else None
                 if (self.stream_adam and mode == "all" and self.timers is None and self.overlap
                         and (self.dp is None or self.dp.can_stream())):
@@ -1253,16 +1260,18 @@ class Engine:
                     self._adam_rest(opt)
                 else:
                     self._update(opt, use_dev=True)
+                if defer:
+                    self.dp.defer_clear = False
             n_nodes = int(self.lib.dmvae_ctx_launch_count(self.ctx)) - l0
-            self._graphs[key] = (g, n_nodes)
-            self._grads_dirty = False
+            self._graphs[key] = (g, n_nodes, defer)
+            self._grads_dirty = False                  # the eager step above cleared them (the capture launched nothing)
             if self.dp is not None:
                 self.dp.mark_updated()
             return
-        g, n_nodes = ent
+        g, n_nodes, self_clearing = ent
         if getattr(self, "_params_dirty", False):
             self.sync_operand_copy()
-        if getattr(self, "_grads_dirty", False):
+        if getattr(self, "_grads_dirty", False) and not self_clearing:
             self.zero_grads()
         if not opt.state_valid:
             opt.upload_state(self.step_count)
@@ -1270,6 +1279,7 @@ class Engine:
             self.klr_dev.fill_(float(kl_ratio))
             self._klr_host = float(kl_ratio)
         g.replay()
+        self._grads_dirty = self_clearing              # a self-clearing graph leaves the consumed gradients for its next replay
         if self.dp is not None:
             self.dp.mark_updated()
         opt.t += 1                     # host mirrors of the device counters
