@@ -300,27 +300,35 @@ struct DpPeers {
   __nv_bfloat16* pbf[8];
 };
 
-// WORLD > 0: compile-time rank count - the peer loads are unrolled and ALL issued before the first add (a run-time loop
-// waits out one NVLink round trip per peer, ~2 us each); WORLD == 0: generic.
-template <int WORLD>
-__global__ void __launch_bounds__(256) dp_reduce_adam_kernel(DpPeers peers, int rank, int world_rt, float* __restrict__ m,
-                                                              float* __restrict__ v, int64_t begin4, int64_t end4,
-                                                              float lr_t, const float* __restrict__ lr_t_dev, float b1,
-                                                              float b2, float eps, int clear_grads) {
+// WORLD > 0: compile-time rank count - the peer loads are unrolled and issued in groups of up to GROUP before the first
+// add (a run-time loop waits out one NVLink round trip per peer, ~2 us each); WORLD == 0: generic.
+// BG: background shape (4-warp blocks, <= 48 registers, groups of 4 loads) that fits beside a resident GEMM CTA.
+template <int WORLD, bool BG>
+__global__ void __launch_bounds__(BG ? 128 : 256, BG ? 10 : 3)
+dp_reduce_adam_kernel(DpPeers peers, int rank, int world_rt, float* __restrict__ m, float* __restrict__ v, int64_t begin4,
+                      int64_t end4, float lr_t, const float* __restrict__ lr_t_dev, float b1, float b2, float eps,
+                      int clear_grads) {
   const int world = WORLD > 0 ? WORLD : world_rt;
+  constexpr int GROUP = WORLD <= 0 ? 1 : (BG && WORLD > 4 ? 4 : WORLD);
+  pdl_wait();                                   // launched like every kernel of the step (programmatic edge)
   if (lr_t_dev) lr_t = __ldg(lr_t_dev);
   int64_t i = begin4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (; i < end4; i += stride) {
     // fixed summation order (rank 0 .. world-1) so that every step is reproducible
-    float4 g;
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
     if (WORLD > 0) {
-      float4 t[WORLD > 0 ? WORLD : 1];
 #pragma unroll
-      for (int r = 0; r < WORLD; ++r) t[r] = reinterpret_cast<const float4*>(peers.grads[r])[i];
-      g = t[0];
+      for (int r0 = 0; r0 < WORLD; r0 += GROUP) {
+        float4 t[GROUP];
 #pragma unroll
-      for (int r = 1; r < WORLD; ++r) { g.x += t[r].x; g.y += t[r].y; g.z += t[r].z; g.w += t[r].w; }
+        for (int r = 0; r < GROUP; ++r) t[r] = reinterpret_cast<const float4*>(peers.grads[r0 + r])[i];
+#pragma unroll
+        for (int r = 0; r < GROUP; ++r) {
+          if (r0 + r == 0) g = t[0];
+          else { g.x += t[r].x; g.y += t[r].y; g.z += t[r].z; g.w += t[r].w; }
+        }
+      }
     } else {
       g = reinterpret_cast<const float4*>(peers.grads[0])[i];
       for (int r = 1; r < world; ++r) {
@@ -349,6 +357,57 @@ __global__ void __launch_bounds__(256) dp_reduce_adam_kernel(DpPeers peers, int 
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Cross-GPU barrier over peer-mapped flag pads (data parallel, mode "p2p").  Every rank owns a pad of
+// [DMVAE_DP_CHANNELS][8] uint32 in symmetric memory; barrier number e of a channel: write e into slot [channel][rank]
+// of every peer's pad (after a system-scope fence), then wait until every slot of the own pad's row has reached e.
+// Epochs are kept per channel in ordinary device memory and advanced by the kernel, so the call captures into CUDA
+// graphs; all ranks issue the same barrier sequence.  A rank that waits longer than ~10 s traps instead of hanging.
+// ---------------------------------------------------------------------------------------------
+struct DpPads {
+  uint32_t* pad[8];
+};
+
+__global__ void __launch_bounds__(32) dp_barrier_kernel(DpPads pads, int rank, int world, uint32_t* __restrict__ epochs,
+                                                        int channel) {
+  pdl_wait();
+  const uint32_t e = epochs[channel] + 1u;
+  const int p = threadIdx.x;
+  if (p < world && p != rank) {
+    __threadfence_system();
+    volatile uint32_t* out = pads.pad[p] + channel * 8 + rank;
+    *out = e;
+    volatile uint32_t* in = pads.pad[rank] + channel * 8 + p;
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    while ((int32_t)(*in - e) < 0) {
+      unsigned long long t1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if (t1 - t0 > 10000000000ull) __trap();
+    }
+    __threadfence_system();
+  }
+  __syncwarp();
+  if (p == 0) epochs[channel] = e;
+}
+
+extern "C" int dmvae_dp_barrier(dmvae_ctx* ctx, int rank, int world, uint32_t* const* pads_host, uint32_t* epochs,
+                                int channel, void* stream) {
+  DMVAE_CHECK_ARG(ctx && pads_host && epochs, "dmvae_dp_barrier: NULL pointer");
+  DMVAE_CHECK_ARG(world >= 1 && world <= 8 && rank >= 0 && rank < world, "dmvae_dp_barrier: world %d rank %d", world, rank);
+  DMVAE_CHECK_ARG(channel >= 0 && channel < DMVAE_DP_CHANNELS, "dmvae_dp_barrier: channel %d outside [0,%d)", channel,
+                  DMVAE_DP_CHANNELS);
+  DpPads pads;
+  memset(&pads, 0, sizeof(pads));
+  for (int r = 0; r < world; ++r) {
+    DMVAE_CHECK_ARG(pads_host[r] != nullptr, "dmvae_dp_barrier: pad of rank %d is NULL", r);
+    pads.pad[r] = pads_host[r];
+  }
+  dmvae_launch(dp_barrier_kernel, dim3(1), dim3(32), 0, (cudaStream_t)stream, true, pads, rank, world, epochs, channel);
+  DMVAE_LAUNCH_CHECK(ctx);
+  return DMVAE_OK;
+}
+
 extern "C" int dmvae_dp_reduce_adam(dmvae_ctx* ctx, int rank, int world, float* const* grads_peers_host,
                                     float* const* params_peers_host, void* const* params_bf16_peers_host, float* m,
                                     float* v, int64_t n, int64_t shard_begin, int64_t shard_end, float lr_t,
@@ -374,12 +433,13 @@ extern "C" int dmvae_dp_reduce_adam(dmvae_ctx* ctx, int rank, int world, float* 
   // DMVAE_ADAM_BACKGROUND: 4-warp blocks that fit beside the GEMM CTAs (see adam_bg_kernel)
   const int threads = (flags & DMVAE_ADAM_BACKGROUND) ? 128 : 256;
   int blocks = (int)min((int64_t)ctx->sm_count * (2048 / threads), (n4 + threads - 1) / threads);
-  auto kern = dp_reduce_adam_kernel<0>;
-  if (world == 2) kern = dp_reduce_adam_kernel<2>;
-  else if (world == 4) kern = dp_reduce_adam_kernel<4>;
-  else if (world == 8) kern = dp_reduce_adam_kernel<8>;
-  kern<<<blocks, threads, 0, (cudaStream_t)stream>>>(peers, rank, world, m, v, shard_begin / 4, shard_end / 4, lr_t, lr_t_dev,
-                                                     beta1, beta2, eps, flags & DMVAE_ADAM_ZERO_GRADS);
+  const bool bg = (flags & DMVAE_ADAM_BACKGROUND) != 0;
+  auto kern = bg ? dp_reduce_adam_kernel<0, true> : dp_reduce_adam_kernel<0, false>;
+  if (world == 2) kern = bg ? dp_reduce_adam_kernel<2, true> : dp_reduce_adam_kernel<2, false>;
+  else if (world == 4) kern = bg ? dp_reduce_adam_kernel<4, true> : dp_reduce_adam_kernel<4, false>;
+  else if (world == 8) kern = bg ? dp_reduce_adam_kernel<8, true> : dp_reduce_adam_kernel<8, false>;
+  dmvae_launch(kern, dim3(blocks), dim3(threads), 0, (cudaStream_t)stream, true, peers, rank, world, m, v, shard_begin / 4,
+               shard_end / 4, lr_t, lr_t_dev, beta1, beta2, eps, flags & DMVAE_ADAM_ZERO_GRADS);
   DMVAE_LAUNCH_CHECK(ctx);
   return DMVAE_OK;
 }

@@ -111,7 +111,10 @@ class DataParallel:
         eng = self.eng
         P = eng.n_params
         nbytes = 4 * P + 4 * P + (2 * P if eng.params_op is not None else 0)
+        pad_off = (nbytes + 255) // 256 * 256             # flag pads of the library's own barrier (dmvae_dp_barrier)
+        nbytes = pad_off + 4 * 8 * self.N_CHANNELS
         buf = symm_mem.empty(nbytes, dtype=torch.uint8, device=eng.device)
+        buf[pad_off:].zero_()
         grp = self.group if self.group is not None else dist.group.WORLD
         hdl = symm_mem.rendezvous(buf, grp)
         params = buf[: 4 * P].view(torch.float32)
@@ -135,7 +138,25 @@ class DataParallel:
         self.master_sharded = eng.params_op is not None
         self._p_ptrs = VP(*[(p if (r == self.rank or not self.master_sharded) else None) for r, p in enumerate(ptrs)])
         self._b_ptrs = VP(*[(p + 8 * P) if eng.params_op is not None else 0 for p in ptrs])
+        self._pad_ptrs = VP(*[p + pad_off for p in ptrs])
+        self._epochs = torch.zeros(self.N_CHANNELS, dtype=torch.int32, device=eng.device)
+        torch.cuda.synchronize(eng.device)
+        hdl.barrier(channel=0)                            # every pad is zeroed before anyone signals into it
+        torch.cuda.synchronize(eng.device)
         self._master_stale = False
+
+    N_CHANNELS = 32
+    # DMVAE_DP_BARRIER=own: the library's own barrier kernel (dmvae_dp_barrier, flag pads in the symmetric buffer)
+    # instead of torch's symmetric-memory barrier.  Same step time at N=2 (0.3312 ms either way); torch's is the default.
+    own_barrier = os.environ.get("DMVAE_DP_BARRIER", "torch") == "own"
+
+    def _barrier(self, ch: int):
+        if self.own_barrier:
+            eng = self.eng
+            self._abi.check(eng.lib.dmvae_dp_barrier(eng.ctx, self.rank, self.world, self._pad_ptrs, self._epochs.data_ptr(),
+                                                     ch, eng._stream()))
+        else:
+            self.hdl.barrier(channel=ch)
 
     # ---- ranges: the flat buffer is exchanged as encoder | decoder | tail (experts, prior tables).  The decoder's
     #      gradients are complete half way through the backward pass, so their exchange overlaps the encoder's
@@ -144,10 +165,13 @@ class DataParallel:
     # soon as its gradients are final (Engine._adam_segment); barrier -> reduce + Adam on the owned shard -> barrier ->
     # local gradient clear run on the side stream beside the remaining gradient GEMMs, in 4-warp blocks that fit next to
     # the GEMM CTAs (see adam_bg_kernel).  Only the first encoder layer's range is left for the end of the step.
-    # EXPERIMENTAL, off by default: measured on 2 x B200 the extra cross-GPU barrier pairs cost more than the overlap
-    # hides (0.357 ms / step with the three large segments streamed, 0.368 with all four, against 0.334 for the single
-    # exchange), and scripts/dp_check.py's fp32 + CUDA-graph configuration did not terminate with it.
-    # DMVAE_DP_STREAM=1 enables it (bf16 tier).
+    # EXPERIMENTAL, off by default.  Measured on 2 x B200 (scripts/step_timeline.py under torchrun): an exchange kernel
+    # that becomes runnable while a gradient GEMM is in full swing - which the opening barrier guarantees - only starts
+    # when that GEMM kernel ends (the same kernel shape does run beside the GEMMs when it becomes runnable exactly at a
+    # kernel boundary, as the N=1 streamed update does), so every streamed segment is late by one GEMM group and pays
+    # two extra cross-GPU barriers: 0.337 ms / step with the two early segments streamed, 0.357 with three, 0.368 with
+    # all four, against 0.331 for the single exchange.  scripts/dp_check.py's fp32 + CUDA-graph configuration did not
+    # terminate with it.  DMVAE_DP_STREAM=1 enables it (bf16 tier).
     stream = os.environ.get("DMVAE_DP_STREAM", "0") == "1"
 
     def can_stream(self) -> bool:
@@ -193,7 +217,7 @@ class DataParallel:
 
     def _exchange(self, opt, lr_t, lr_dev, ridxs, ch, background=False):
         eng, abi = self.eng, self._abi
-        self.hdl.barrier(channel=ch)                      # every rank's gradients of these ranges are complete
+        self._barrier(ch)                                 # every rank's gradients of these ranges are complete
         for ridx in ridxs:
             b, e = self.range_shard(ridx)
             if e <= b:
@@ -203,7 +227,7 @@ class DataParallel:
                                                    self._b_ptrs, m.data_ptr(), v.data_ptr(), eng.n_params, b, e, lr_t,
                                                    lr_dev, opt.beta1, opt.beta2, opt.eps, 2 if background else 0,
                                                    eng._stream()))
-        self.hdl.barrier(channel=ch + 1)                  # every replica updated, every gradient shard consumed
+        self._barrier(ch + 1)                             # every replica updated, every gradient shard consumed
         # clear the local gradients of these ranges (split-K accumulates into them): local HBM, not 7/8 remote stores
         if self.defer_clear:
             return

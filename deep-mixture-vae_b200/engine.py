@@ -1039,8 +1039,11 @@ class Engine:
         names = self._stream_plan().get(key)
         if not names:
             return
-        if self.dp is not None and key.startswith("enc:"):
-            return                                   # a separate exchange (two cross-GPU barriers) right before the final one only lengthens the tail
+        if self.dp is not None and (key.startswith("enc") or key == "ench"):
+            # measured (2 x B200 timelines): an exchange kernel that becomes runnable while a gradient GEMM is in full swing
+            # only starts at that GEMM's end, so a segment that is final late in the backward pass would be exchanged
+            # after the last GEMM anyway - plus two more cross-GPU barriers; those go with the final exchange
+            return
         opt, done = self._adam_live
         merged = self._merged_ranges(names)
 

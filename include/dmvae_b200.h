@@ -259,6 +259,12 @@ int dmvae_dp_reduce_adam(dmvae_ctx* ctx, int rank, int world, float* const* grad
                          int flags /* DMVAE_ADAM_ZERO_GRADS: clear the consumed shard in every replica (0: every rank clears its
                                       own gradient buffer after the closing barrier); DMVAE_ADAM_BACKGROUND: small blocks */,
                          void* stream);
+/* Cross-GPU barrier over peer-mapped flag pads: pads_host[r] = rank r's pad, uint32 [DMVAE_DP_CHANNELS][8], zero-initialised,
+ * in symmetric memory; epochs = uint32 [DMVAE_DP_CHANNELS] in ordinary device memory, zero-initialised.  Every rank must
+ * issue the same sequence of (channel) barriers; barriers on different channels may be in flight on different streams. */
+#define DMVAE_DP_CHANNELS 32
+int dmvae_dp_barrier(dmvae_ctx* ctx, int rank, int world, uint32_t* const* pads_host, uint32_t* epochs, int channel,
+                     void* stream);
 /* params_peers_host[r] may be NULL for r != rank when params_bf16_peers_host[r] is given: the fp32 master copy of a
  * shard then lives on its owner only (the bf16 operand copy, which is all the GEMMs read, is still replicated). */
 /* zero a fp32 buffer (gradient accumulators) */

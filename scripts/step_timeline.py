@@ -15,11 +15,22 @@ from dmvae_b200.engine import Engine  # noqa: E402
 
 
 def main():
+    """Single GPU: python scripts/step_timeline.py.  Data parallel: torchrun --nproc-per-node N scripts/step_timeline.py
+    (rank 0 prints its own timeline, which then includes the cross-GPU barriers and the exchange kernel)."""
     B = bench.BATCH_PER_GPU
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+        dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ["LOCAL_RANK"])))
     eng = Engine(model="dmvae", input_type="binary", input_dim=bench.D, latent_dim=bench.L, n_classes=bench.K, trunk=bench.TRUNK,
                  head=bench.HEAD, decoder=bench.DEC, name="dmvae", gemm_dtype="bf16", max_rows=B, seed=0)
+    if world > 1:
+        from dmvae_b200.dp import DataParallel
+        DataParallel(eng, mode="auto")
     opt = eng.optimizer("train", 0.002)
-    xs = torch.from_numpy(bench.synth_batches(B)).cuda()
+    xs = torch.from_numpy(bench.synth_batches(B, seed=1 + rank)).cuda()
     for _ in range(5):
         eng.train_step(xs, B, opt)
     torch.cuda.synchronize()
@@ -27,6 +38,11 @@ def main():
         for _ in range(3):
             eng.train_step(xs, B, opt)
         torch.cuda.synchronize()
+    if world > 1:
+        torch.distributed.barrier()
+        if rank != 0:
+            torch.cuda.synchronize()
+            os._exit(0)
     out = os.path.join(ROOT, "gpurun_out", "step_trace.json")
     prof.export_chrome_trace(out)
     ev = [e for e in json.load(open(out))["traceEvents"] if e.get("cat") in ("kernel", "gpu_memcpy", "gpu_memset")]
@@ -43,6 +59,9 @@ def main():
     for e in rows:
         nm = e["name"].replace("(anonymous namespace)::", "").split("(")[0][:60]
         print("%8.1f %7.1f  s%-3s %s  grid=%s" % (e["ts"] - t0, e["dur"], e["args"].get("stream", "?"), nm, e["args"].get("grid", "")))
+    if world > 1:
+        sys.stdout.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":
