@@ -250,6 +250,7 @@ def run_ours(args):
                                "(BASELINE.json configs[1])",
                    "batch_per_gpu": B, "global_batch": world * B, "hidden": "784-500-500-2000 / 2000-500-500-784",
                    "parallelism": "dp%d" % world if world > 1 else "single",
+                   "exchange": None if dp is None else (dp.mode + ("+nvls" if getattr(dp, "_mc", 0) else "")),
                    "l2": "per-step working set ~240 MB (> 126 MB L2); inputs rotate over 16 resident batches",
                    "noise": "device Philox4x32-10", "optimizer": "Adam (TF semantics), every step"},
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": world * B * D, "d2h_bytes_per_step": world * 16,

@@ -119,6 +119,8 @@ SIGNATURES = {
     "dmvae_dp_reduce_adam": (c_int, [c_void_p, c_int, c_int, C.POINTER(c_void_p), C.POINTER(c_void_p),
                                      C.POINTER(c_void_p), c_void_p, c_void_p, c_int64, c_int64, c_int64, c_float, c_void_p,
                                      c_float, c_float, c_float, c_int, c_void_p]),
+    "dmvae_dp_reduce_adam_mc": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64,
+                                        c_int64, c_float, c_void_p, c_float, c_float, c_float, c_void_p]),
     "dmvae_dp_barrier": (c_int, [c_void_p, c_int, c_int, C.POINTER(c_void_p), c_void_p, c_int, c_void_p]),
     "dmvae_zero_f32": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "dmvae_cast_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),

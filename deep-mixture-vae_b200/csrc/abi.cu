@@ -358,6 +358,73 @@ dp_reduce_adam_kernel(DpPeers peers, int rank, int world_rt, float* __restrict__
 }
 
 // ---------------------------------------------------------------------------------------------
+// NVSwitch (NVLS) form of the exchange: the gradient sum is done IN THE SWITCH by one multimem.ld_reduce on the
+// multicast address of the symmetric buffer (inbound bytes per rank: its own shard once, instead of that shard from
+// every peer), and the updated bf16 operand copy / fp32 parameters go out as ONE multimem.st that the switch
+// replicates into every replica (outbound: the shard once instead of N times).  The switch's reduction order is fixed
+// by the topology, not rank order 0..N-1: results are reproducible run to run but differ from the peer-pointer kernel
+// in the last bits.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256, 3)
+dp_reduce_adam_mc_kernel(const float* __restrict__ mc_grads, float* __restrict__ mc_params /* or NULL: master stays local */,
+                         __nv_bfloat16* __restrict__ mc_pbf /* or NULL */, float* __restrict__ params_local,
+                         float* __restrict__ m, float* __restrict__ v, int64_t begin4, int64_t end4, float lr_t,
+                         const float* __restrict__ lr_t_dev, float b1, float b2, float eps) {
+  pdl_wait();
+  if (lr_t_dev) lr_t = __ldg(lr_t_dev);
+  int64_t i = begin4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < end4; i += stride) {
+    float4 g;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(g.x), "=f"(g.y), "=f"(g.z), "=f"(g.w)
+                 : "l"(reinterpret_cast<const float4*>(mc_grads) + i)
+                 : "memory");
+    float4 p = reinterpret_cast<float4*>(params_local)[i];
+    const int64_t li = i - begin4;
+    float4 mm = reinterpret_cast<float4*>(m)[li];
+    float4 vv = reinterpret_cast<float4*>(v)[li];
+    adam_update4(p, g, mm, vv, lr_t, b1, b2, eps, 1.f);
+    reinterpret_cast<float4*>(m)[li] = mm;
+    reinterpret_cast<float4*>(v)[li] = vv;
+    if (mc_params)
+      asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(reinterpret_cast<float4*>(mc_params) + i),
+                   "f"(p.x), "f"(p.y), "f"(p.z), "f"(p.w)
+                   : "memory");
+    else
+      reinterpret_cast<float4*>(params_local)[i] = p;
+    if (mc_pbf) {
+      __nv_bfloat162 lo = __floats2bfloat162_rn(p.x, p.y), hi = __floats2bfloat162_rn(p.z, p.w);
+      asm volatile("multimem.st.relaxed.sys.global.v2.bf16x2 [%0], {%1, %2};" ::"l"(reinterpret_cast<uint2*>(mc_pbf) + i),
+                   "r"(*reinterpret_cast<uint32_t*>(&lo)), "r"(*reinterpret_cast<uint32_t*>(&hi))
+                   : "memory");
+    }
+  }
+}
+
+extern "C" int dmvae_dp_reduce_adam_mc(dmvae_ctx* ctx, const float* mc_grads, float* mc_params, void* mc_params_bf16,
+                                       float* params_local, float* m, float* v, int64_t n, int64_t shard_begin,
+                                       int64_t shard_end, float lr_t, const float* lr_t_dev, float beta1, float beta2,
+                                       float eps, void* stream) {
+  DMVAE_CHECK_ARG(ctx && mc_grads && params_local && m && v, "dmvae_dp_reduce_adam_mc: NULL pointer");
+  DMVAE_CHECK_ARG(mc_params || mc_params_bf16, "dmvae_dp_reduce_adam_mc: a multicast fp32 or bf16 parameter pointer is required");
+  DMVAE_CHECK_ARG(shard_begin % 4 == 0 && shard_end % 4 == 0 && 0 <= shard_begin && shard_begin <= shard_end && shard_end <= n,
+                  "dmvae_dp_reduce_adam_mc: shard [%lld,%lld) must be 4-aligned and inside [0,%lld)", (long long)shard_begin,
+                  (long long)shard_end, (long long)n);
+  DMVAE_CHECK_ARG((((uintptr_t)mc_grads | (uintptr_t)mc_params | (uintptr_t)params_local | (uintptr_t)m | (uintptr_t)v) & 15) == 0 &&
+                      ((uintptr_t)mc_params_bf16 & 7) == 0,
+                  "dmvae_dp_reduce_adam_mc: buffers must be 16-byte aligned");
+  if (shard_end == shard_begin) return DMVAE_OK;
+  int64_t n4 = (shard_end - shard_begin) / 4;
+  int blocks = (int)min((int64_t)ctx->sm_count * 8, (n4 + 255) / 256);
+  dmvae_launch(dp_reduce_adam_mc_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, true, mc_grads, mc_params,
+               (__nv_bfloat16*)mc_params_bf16, params_local, m, v, shard_begin / 4, shard_end / 4, lr_t, lr_t_dev, beta1, beta2,
+               eps);
+  DMVAE_LAUNCH_CHECK(ctx);
+  return DMVAE_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Cross-GPU barrier over peer-mapped flag pads (data parallel, mode "p2p").  Every rank owns a pad of
 // [DMVAE_DP_CHANNELS][8] uint32 in symmetric memory; barrier number e of a channel: write e into slot [channel][rank]
 // of every peer's pad (after a system-scope fence), then wait until every slot of the own pad's row has reached e.

@@ -139,6 +139,9 @@ class DataParallel:
         self._p_ptrs = VP(*[(p if (r == self.rank or not self.master_sharded) else None) for r, p in enumerate(ptrs)])
         self._b_ptrs = VP(*[(p + 8 * P) if eng.params_op is not None else 0 for p in ptrs])
         self._pad_ptrs = VP(*[p + pad_off for p in ptrs])
+        # NVSwitch multicast mapping of the same buffer (0 when the fabric / driver does not offer it)
+        self._mc = int(getattr(hdl, "multicast_ptr", 0) or 0) if self.use_multicast else 0
+        self._mc_off = (4 * P, 8 * P)
         self._epochs = torch.zeros(self.N_CHANNELS, dtype=torch.int32, device=eng.device)
         torch.cuda.synchronize(eng.device)
         hdl.barrier(channel=0)                            # every pad is zeroed before anyone signals into it
@@ -146,6 +149,12 @@ class DataParallel:
         self._master_stale = False
 
     N_CHANNELS = 32
+    # DMVAE_DP_MULTICAST=1: in-switch reduction (multimem.ld_reduce) + broadcast store (multimem.st) through the NVSwitch
+    # multicast mapping of the symmetric buffer instead of the peer-pointer kernel.  Correct (scripts/dp_check.py passes
+    # with it) but measured SLOWER at N=2 (0.348 vs 0.331 ms / step): every GPU still serves its whole gradient buffer to
+    # the switch (outbound bytes are unchanged, only inbound shrinks), the switch adds latency, and at N=2 the local
+    # half of the sum also crosses NVLink.  Off by default; the peer-pointer kernel also keeps the rank-order sum.
+    use_multicast = os.environ.get("DMVAE_DP_MULTICAST", "0") == "1"
     # DMVAE_DP_BARRIER=own: the library's own barrier kernel (dmvae_dp_barrier, flag pads in the symmetric buffer)
     # instead of torch's symmetric-memory barrier.  Same step time at N=2 (0.3312 ms either way); torch's is the default.
     own_barrier = os.environ.get("DMVAE_DP_BARRIER", "torch") == "own"
@@ -223,6 +232,14 @@ class DataParallel:
             if e <= b:
                 continue
             m, v = self._opt_shard_state(opt, ridx)
+            if getattr(self, "_mc", 0) and not background:
+                # in-switch reduction + broadcast store (NVLS); the fp32 master is broadcast only when it is replicated
+                mc = self._mc
+                abi.check(eng.lib.dmvae_dp_reduce_adam_mc(
+                    eng.ctx, mc + self._mc_off[0], None if self.master_sharded else mc,
+                    (mc + self._mc_off[1]) if eng.params_op is not None else None, eng.params.data_ptr(), m.data_ptr(),
+                    v.data_ptr(), eng.n_params, b, e, lr_t, lr_dev, opt.beta1, opt.beta2, opt.eps, eng._stream()))
+                continue
             abi.check(eng.lib.dmvae_dp_reduce_adam(eng.ctx, self.rank, self.world, self._g_ptrs, self._p_ptrs,
                                                    self._b_ptrs, m.data_ptr(), v.data_ptr(), eng.n_params, b, e, lr_t,
                                                    lr_dev, opt.beta1, opt.beta2, opt.eps, 2 if background else 0,

@@ -259,6 +259,14 @@ int dmvae_dp_reduce_adam(dmvae_ctx* ctx, int rank, int world, float* const* grad
                          int flags /* DMVAE_ADAM_ZERO_GRADS: clear the consumed shard in every replica (0: every rank clears its
                                       own gradient buffer after the closing barrier); DMVAE_ADAM_BACKGROUND: small blocks */,
                          void* stream);
+/* NVSwitch form of dmvae_dp_reduce_adam: mc_* are MULTICAST addresses of the ranks' symmetric buffers (gradients, fp32
+ * parameters or NULL, bf16 operand copy or NULL).  The gradient shard is summed in the switch (multimem.ld_reduce), the
+ * update is applied to the owned shard [shard_begin, shard_end) with the local Adam slots m, v (indexed from the shard's
+ * start), and the new parameters are broadcast through the switch (multimem.st).  With mc_params == NULL the fp32 master
+ * of the shard is written to params_local only.  Bracket with cross-rank barriers like dmvae_dp_reduce_adam. */
+int dmvae_dp_reduce_adam_mc(dmvae_ctx* ctx, const float* mc_grads, float* mc_params, void* mc_params_bf16,
+                            float* params_local, float* m, float* v, int64_t n, int64_t shard_begin, int64_t shard_end,
+                            float lr_t, const float* lr_t_dev, float beta1, float beta2, float eps, void* stream);
 /* Cross-GPU barrier over peer-mapped flag pads: pads_host[r] = rank r's pad, uint32 [DMVAE_DP_CHANNELS][8], zero-initialised,
  * in symmetric memory; epochs = uint32 [DMVAE_DP_CHANNELS] in ordinary device memory, zero-initialised.  Every rank must
  * issue the same sequence of (channel) barriers; barriers on different channels may be in flight on different streams. */
