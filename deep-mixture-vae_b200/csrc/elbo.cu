@@ -769,17 +769,31 @@ __global__ void __launch_bounds__(kFastThreads, 4) elbo_rowtile_kernel(const Elb
     const uint32_t xt_w = xt + (uint32_t)(warp * kFastRW * p.xrow), dt_w = dt + (uint32_t)(warp * kFastRW * p.drow);
     // contiguous tiles (row pitch == row bytes) move as ONE bulk copy per tensor and CTA: the TMA unit's cost is per
     // request (~150 cycles measured), so 48 row-sized copies per CTA had made it the bottleneck
+    // ... and as TWO halves (rows 0-7 for warps 0-3, rows 8-15 for warps 4-7), each with its own mbarrier and its own
+    // store: the first half's warps start computing while the second half is still in flight, and its gradient rows
+    // leave while the second half is still being computed.
     const bool whole = p.contig != 0;
-    const uint32_t bar_w = smem_addr_u32(&bars[whole ? 0 : warp]);
+    constexpr int kHalfRows = kFastRows / 2;
+    const int half = warp >> 2;
+    const int nrows_h0 = min(nrows_cta, kHalfRows), nrows_h1 = nrows_cta - nrows_h0;
+    const uint32_t bar_w = smem_addr_u32(&bars[whole ? half : warp]);
     if (lane == 0 && (!whole || warp == 0)) {
       asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_w), "r"(1));
+      if (whole) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr_u32(&bars[1])), "r"(1));
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
       const uint32_t dbytes = (uint32_t)(D * (int)sizeof(TD));
       if (whole) {
-        const uint32_t xb = (uint32_t)(nrows_cta * p.xrow), db = (uint32_t)(nrows_cta * p.drow);
+        const uint32_t xb = (uint32_t)(nrows_h0 * p.xrow), db = (uint32_t)(nrows_h0 * p.drow);
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_w), "r"(xb + db) : "memory");
         bulk_g2s(xt, reinterpret_cast<const uint8_t*>(a.X) + (int64_t)row0 * p.xrow, xb, bar_w);
         bulk_g2s(dt, reinterpret_cast<const uint8_t*>(a.decoded) + (int64_t)row0 * p.drow, db, bar_w);
+        if (nrows_h1 > 0) {
+          const uint32_t bar1 = smem_addr_u32(&bars[1]);
+          const uint32_t xb1 = (uint32_t)(nrows_h1 * p.xrow), db1 = (uint32_t)(nrows_h1 * p.drow);
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar1), "r"(xb1 + db1) : "memory");
+          bulk_g2s(xt + xb, reinterpret_cast<const uint8_t*>(a.X) + (int64_t)(row0 + kHalfRows) * p.xrow, xb1, bar1);
+          bulk_g2s(dt + db, reinterpret_cast<const uint8_t*>(a.decoded) + (int64_t)(row0 + kHalfRows) * p.drow, db1, bar1);
+        }
       } else {
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_w),
                      "r"((uint32_t)nrows_w * ((uint32_t)p.xrow + dbytes))
@@ -792,9 +806,9 @@ __global__ void __launch_bounds__(kFastThreads, 4) elbo_rowtile_kernel(const Elb
         }
       }
     }
-    if (whole) asm volatile("bar.sync 3, 256;" ::: "memory");   // the barrier word is initialised before anyone polls it
+    if (whole) asm volatile("bar.sync 3, 256;" ::: "memory");   // the barrier words are initialised before anyone polls them
     else __syncwarp();
-    mbar_wait_parity(bar_w, 0);
+    if (nrows_w > 0) mbar_wait_parity(bar_w, 0);
     // The warp's two rows are ONE list of 8-element chunks, chunk c = lane + 32 i (no per-row tail iteration).  A lane's
     // chunks are ordered by row, so the row sums are plain per-lane accumulators that are parked once, at the
     // iteration where the lane crosses into the second row.
@@ -859,9 +873,14 @@ __global__ void __launch_bounds__(kFastThreads, 4) elbo_rowtile_kernel(const Elb
     asm volatile("bar.arrive 1, %0;" ::"n"(kFastThreads) : "memory");         // R_s written (latent warps wait on it)
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     if (whole) {
-      asm volatile("bar.sync 3, 256;" ::: "memory");            // every slab of the tile is final
-      if (warp == 0 && lane == 0) {
-        bulk_s2g(reinterpret_cast<uint8_t*>(a.d_decoded) + (int64_t)row0 * p.drow, dt, (uint32_t)(nrows_cta * p.drow));
+      // every slab of this half is final (named barrier 4 / 5, the half's four warps)
+      if (half == 0) asm volatile("bar.sync 4, 128;" ::: "memory");
+      else asm volatile("bar.sync 5, 128;" ::: "memory");
+      const int nrows_h = half == 0 ? nrows_h0 : nrows_h1;
+      if ((warp & 3) == 0 && lane == 0 && nrows_h > 0) {
+        const int64_t r0h = row0 + half * kHalfRows;
+        bulk_s2g(reinterpret_cast<uint8_t*>(a.d_decoded) + r0h * p.drow, dt + (uint32_t)(half * kHalfRows * p.drow),
+                 (uint32_t)(nrows_h * p.drow));
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
       }
