@@ -406,6 +406,45 @@ def test_adam_tf_semantics(lib, ctx):
     assert np.all(p.cpu().numpy()[::7] == th[::7])          # zero gradient from the start -> never moves
 
 
+def test_adam_launch_shapes_and_exchange_kernel_agree(lib, ctx):
+    """The background launch shape of Adam (4-warp blocks that fit beside a GEMM CTA) and the data-parallel exchange
+    kernel with world = 1 (both launch shapes) are the same arithmetic as dmvae_adam: bit-identical parameters, slots,
+    bf16 operand copy; a sub-range call (pointer offsets) only touches its range."""
+    from dmvae_b200 import _abi
+    rs = np.random.RandomState(11)
+    n = 64 * 64 * 3 + 64
+    th, g = rs.randn(n).astype(np.float32), (rs.randn(n) * 1e-2).astype(np.float32)
+    m0, v0 = (rs.randn(n) * 1e-3).astype(np.float32), (rs.rand(n) * 1e-4).astype(np.float32)
+
+    def run(kind):
+        p, gr, m, v = dev(th), dev(g), dev(m0), dev(v0)
+        pb = torch.zeros(n, dtype=torch.bfloat16, device="cuda")
+        if kind in ("fg", "bg"):
+            _abi.check(lib.dmvae_adam(ctx, p.data_ptr(), gr.data_ptr(), m.data_ptr(), v.data_ptr(), pb.data_ptr(), n, 1.5e-3,
+                                      None, 0.9, 0.999, 1e-8, 1.0, 1 if kind == "fg" else 3, stream()))
+        elif kind == "range":                    # three calls over disjoint sub-ranges, mixed shapes
+            for lo, hi, fl in ((0, 4096, 3), (4096, 8192 + 64, 1), (8192 + 64, n, 3)):
+                _abi.check(lib.dmvae_adam(ctx, p.data_ptr() + 4 * lo, gr.data_ptr() + 4 * lo, m.data_ptr() + 4 * lo,
+                                          v.data_ptr() + 4 * lo, pb.data_ptr() + 2 * lo, hi - lo, 1.5e-3, None, 0.9, 0.999,
+                                          1e-8, 1.0, fl, stream()))
+        else:                                    # exchange kernel, one rank: its own buffers are the only "peers"
+            VP = C.c_void_p * 1
+            _abi.check(lib.dmvae_dp_reduce_adam(ctx, 0, 1, VP(gr.data_ptr()), VP(p.data_ptr()), VP(pb.data_ptr()),
+                                                m.data_ptr(), v.data_ptr(), n, 0, n, 1.5e-3, None, 0.9, 0.999, 1e-8,
+                                                1 | (2 if kind == "dp_bg" else 0), stream()))
+        torch.cuda.synchronize()
+        return [t.clone() for t in (p, m, v, pb, gr)]
+
+    ref = run("fg")
+    assert float(ref[4].abs().max()) == 0.0
+    for kind in ("bg", "range", "dp", "dp_bg"):
+        got = run(kind)
+        for a, b in zip(ref, got):
+            assert torch.equal(a, b), kind
+    assert lib.dmvae_adam(ctx, ref[0].data_ptr(), ref[4].data_ptr(), ref[1].data_ptr(), ref[2].data_ptr(), None, n, 1e-3, None,
+                          0.9, 0.999, 1e-8, 1.0, 8, stream()) != 0          # unknown flag bits are rejected
+
+
 def test_step_tick_and_device_lr(lib, ctx):
     """CUDA-graph replay reads Adam's lr_t and the Philox step from device memory."""
     from dmvae_b200 import _abi
