@@ -183,7 +183,9 @@ class VAE:
             elif mode == "prior":
                 rs = 0.0                  # minimize(latent_loss, var_list = c-head)
                 klr = 1.0
-            eng.train_step(Xd, rows, opt, eps_d, gum_d, klr, mode, rs)
+            # session.run feeds are transient device tensors: a captured graph keyed on their address would be rebuilt for
+            # every new allocation, so only the epoch loop's persistent staging buffers are captured (Engine.run_epoch)
+            eng.train_step(Xd, rows, opt, eps_d, gum_d, klr, mode, rs, graph=False)
         else:
             need_full = any(n not in ("logits", "mean", "log_var") for n in names) or eng.model == "vade"
             if need_full:

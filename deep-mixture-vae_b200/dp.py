@@ -137,6 +137,7 @@ class DataParallel:
         # master of a shard stays with its owner (Adam's only reader) and is fetched on demand (gather_master)
         self.master_sharded = eng.params_op is not None
         self._p_ptrs = VP(*[(p if (r == self.rank or not self.master_sharded) else None) for r, p in enumerate(ptrs)])
+        self._p_ptrs_full = VP(*ptrs)                     # every replica's fp32 master (prior tables: read by the ELBO kernel)
         self._b_ptrs = VP(*[(p + 8 * P) if eng.params_op is not None else 0 for p in ptrs])
         self._pad_ptrs = VP(*[p + pad_off for p in ptrs])
         # NVSwitch multicast mapping of the same buffer (0 when the fabric / driver does not offer it)
@@ -232,18 +233,27 @@ class DataParallel:
             if e <= b:
                 continue
             m, v = self._opt_shard_state(opt, ridx)
-            if getattr(self, "_mc", 0) and not background:
-                # in-switch reduction + broadcast store (NVLS); the fp32 master is broadcast only when it is replicated
-                mc = self._mc
-                abi.check(eng.lib.dmvae_dp_reduce_adam_mc(
-                    eng.ctx, mc + self._mc_off[0], None if self.master_sharded else mc,
-                    (mc + self._mc_off[1]) if eng.params_op is not None else None, eng.params.data_ptr(), m.data_ptr(),
-                    v.data_ptr(), eng.n_params, b, e, lr_t, lr_dev, opt.beta1, opt.beta2, opt.eps, eng._stream()))
-                continue
-            abi.check(eng.lib.dmvae_dp_reduce_adam(eng.ctx, self.rank, self.world, self._g_ptrs, self._p_ptrs,
-                                                   self._b_ptrs, m.data_ptr(), v.data_ptr(), eng.n_params, b, e, lr_t,
-                                                   lr_dev, opt.beta1, opt.beta2, opt.eps, 2 if background else 0,
-                                                   eng._stream()))
+            # The prior tables (the tail of the flat buffer) are read in fp32 by the fused ELBO kernel on EVERY rank
+            # (Engine._elbo_args), so their fp32 master must stay replicated even when the rest of the master is kept by
+            # its owner only: the part of the shard that overlaps them is exchanged with all fp32 peer pointers set.
+            t0 = eng.off_means if self.master_sharded else e
+            pieces = [(b, min(e, t0), False), (max(b, t0), e, True)]
+            for pb, pe, full in pieces:
+                if pe <= pb:
+                    continue
+                mo, vo = m.data_ptr() + 4 * (pb - b), v.data_ptr() + 4 * (pb - b)
+                if getattr(self, "_mc", 0) and not background:
+                    # in-switch reduction + broadcast store (NVLS); the fp32 master is broadcast only when it is replicated
+                    mc = self._mc
+                    abi.check(eng.lib.dmvae_dp_reduce_adam_mc(
+                        eng.ctx, mc + self._mc_off[0], mc if (full or not self.master_sharded) else None,
+                        (mc + self._mc_off[1]) if eng.params_op is not None else None, eng.params.data_ptr(), mo, vo,
+                        eng.n_params, pb, pe, lr_t, lr_dev, opt.beta1, opt.beta2, opt.eps, eng._stream()))
+                    continue
+                abi.check(eng.lib.dmvae_dp_reduce_adam(eng.ctx, self.rank, self.world, self._g_ptrs,
+                                                       self._p_ptrs_full if full else self._p_ptrs, self._b_ptrs, mo, vo,
+                                                       eng.n_params, pb, pe, lr_t, lr_dev, opt.beta1, opt.beta2, opt.eps,
+                                                       2 if background else 0, eng._stream()))
         self._barrier(ch + 1)                             # every replica updated, every gradient shard consumed
         # clear the local gradients of these ranges (split-K accumulates into them): local HBM, not 7/8 remote stores
         if self.defer_clear:

@@ -339,6 +339,8 @@ class Engine:
         if name in self.dead_vars:
             self.dead_values[name] = value.reshape(self.dead_vars[name]).copy()
             return
+        if self.dp is not None:
+            self.dp.gather_master()            # the recast below reads the whole fp32 buffer: peers' shards must be current
         vv = self.vars[name]
         if tuple(value.shape) != tuple(vv.shape):
             value = value.reshape(vv.shape)
@@ -387,6 +389,8 @@ class Engine:
 
     def sync_operand_copy(self) -> None:
         """Refresh the bf16 operand copy of the parameters (after loading variables)."""
+        if self.dp is not None:
+            self.dp.gather_master()
         if self.params_op is not None:
             _abi.check(self.lib.dmvae_cast_bf16(self.ctx, self.params.data_ptr(), self.params_op.data_ptr(),
                                                 self.n_params, self._stream()))
@@ -399,6 +403,9 @@ class Engine:
         if rows <= self.max_rows:
             return
         self.max_rows = rows
+        # captured graphs and the epoch staging hold the old buffers' addresses: drop them with the buffers
+        self._graphs = {}
+        self._epoch_key = None
         dev, t = self.device, self.tdt
         B = rows
         z = lambda cols, dt=t: torch.zeros(B, cols, dtype=dt, device=dev)
@@ -430,7 +437,8 @@ class Engine:
         self.dz_gamma = z(self.L, f32)
         self.w_scratch = z(self.K, f32)
         self.f_scratch = z(2 * self.L, f32)
-        self.loss_out = torch.zeros(4, dtype=f32, device=dev)
+        if getattr(self, "loss_out", None) is None:
+            self.loss_out = torch.zeros(4, dtype=f32, device=dev)      # allocated once: fetches keep reading the same scalar block
         ws = int(self.lib.dmvae_elbo_reduce_workspace(B, self.L, self.K))
         self.red_ws = torch.zeros(max(ws, 4), dtype=f32, device=dev)
         self.x_stage: Dict[int, torch.Tensor] = {}
@@ -1101,7 +1109,10 @@ class Engine:
             self.decode(rows)
         flags = dict(all=(True, True, True, True), vae=(True, True, False, True), prior=(False, False, True, False))[mode]
         klr_dev = self.klr_dev.data_ptr() if (dev_state is not None and mode == "all") else None
-        self.elbo(X, xdt, rows, kl_ratio, inv_global_batch, recon_scale, prior_grads=(mode == "all"), klr_dev=klr_dev)
+        # prior-table gradients only when a full training step will consume them: an evaluation pass (backward=False) or
+        # a pre-training mode must leave the means / log_vars gradient slots alone (base_models.py:307-321 never touch them)
+        self.elbo(X, xdt, rows, kl_ratio, inv_global_batch, recon_scale, prior_grads=(backward and mode == "all"),
+                  klr_dev=klr_dev)
         if backward:
             self.backward(rows, train_decoder=flags[0], train_z=flags[1], train_c=flags[2], train_trunk=flags[3])
             self._grads_dirty = True

@@ -97,6 +97,45 @@ def main():
     if rank == 0:
         print("bf16 sharded master: replicas identical %s, master==operand copy %s, parameters moved %.2e -> %s" %
               (same, cast_ok, moved, "OK" if good else "MISMATCH"), flush=True)
+    eng.close()
+    # bf16 tier, several captured steps: the prior tables are read in fp32 by the fused ELBO kernel on EVERY rank, so
+    # every rank's LOCAL fp32 copy of them (no gather_master) must follow the owner's update, and the N-GPU loss / tables
+    # must track the 1-GPU run on the concatenated batch (bf16 split-K sums are order-dependent: loose bars)
+    eng = make("bf16", Bl)
+    dp = DataParallel(eng, mode="p2p")
+    opt = eng.optimizer("train", 0.002)
+    t_init = eng.params[eng.off_means:].clone()
+    losses = []
+    for i in range(6):
+        dp.train_step(torch.tensor(Xg[i % 3, rank * Bl:(rank + 1) * Bl], device="cuda"), Bl, opt)
+        t = eng.loss_out.clone()
+        dist.all_reduce(t)
+        losses.append(float(t[3]))
+    torch.cuda.synchronize()
+    dist.barrier()
+    local_tab = eng.params[eng.off_means:].clone()            # this rank's own fp32 copy, NOT gathered
+    tabs = [torch.zeros_like(local_tab) for _ in range(world)]
+    dist.all_gather(tabs, local_tab)
+    tab_same = all(torch.equal(tabs[0], t) for t in tabs)
+    tab_moved = float((local_tab - t_init).abs().max())
+    good = bool(tab_same and tab_moved > 1e-3)
+    if rank == 0:
+        ref = make("bf16", Bl * world)
+        ro = ref.optimizer("train", 0.002)
+        rl = []
+        for i in range(6):
+            ref.train_step(torch.tensor(Xg[i % 3], device="cuda"), Bl * world, ro)
+            rl.append(float(ref.loss_out[3]))
+        torch.cuda.synchronize()
+        lerr = max(abs(a - b) / abs(b) for a, b in zip(losses, rl))
+        tdiff = float((ref.params[ref.off_means:] - local_tab).abs().mean())
+        good = good and lerr < 5e-3 and tdiff < 2e-3        # 6 steps x lr 2e-3: stale tables would sit ~1e-2 away
+        print("bf16 %d-GPU vs 1-GPU over 6 steps: local prior tables identical on all ranks %s (moved %.2e), loss rel err "
+              "%.2e, mean |table - 1-GPU table| %.2e -> %s" % (world, tab_same, tab_moved, lerr, tdiff, "OK" if good else "MISMATCH"),
+              flush=True)
+        ref.close()
+    ok = ok and good
+    if rank == 0:
         print("DP_CHECK", "PASS" if ok else "FAIL", flush=True)
     dist.destroy_process_group()
 

@@ -31,7 +31,8 @@ def time_elbo(lib, ctx, B, D=784, L=10, K=10, iters=20, check=False, log=print):
         dec = (torch.randn(B, Dp, device="cuda") * 2).to(torch.bfloat16)
         ddec = torch.empty_like(dec)
         sets.append((X, dec, ddec))
-    zh = torch.randn(B, 64, device="cuda") * 0.5
+    Zp = (2 * L + 63) // 64 * 64
+    zh = torch.randn(B, Zp, device="cuda") * 0.5
     lg = torch.randn(B, Kp, device="cuda")
     dlg = torch.empty(B, Kp, dtype=torch.bfloat16, device="cuda")
     pm, pl = torch.randn(K, L, device="cuda"), torch.randn(K, L, device="cuda") * 0.3
@@ -44,7 +45,7 @@ def time_elbo(lib, ctx, B, D=784, L=10, K=10, iters=20, check=False, log=print):
         ea.mode, ea.input_type, ea.rows, ea.D, ea.L, ea.K = 0, 0, B, D, L, K
         ea.X, ea.x_dtype, ea.ldx = X.data_ptr(), 2, D
         ea.decoded, ea.dec_dtype, ea.ld_dec = dec.data_ptr(), 1, Dp
-        ea.mean, ea.log_var, ea.ld_zh = zh.data_ptr(), zh.data_ptr() + 4 * L, 64
+        ea.mean, ea.log_var, ea.ld_zh = zh.data_ptr(), zh.data_ptr() + 4 * L, Zp
         ea.logits, ea.ld_logits = lg.data_ptr(), Kp
         ea.d_logits, ea.dlogits_dtype, ea.ld_dlogits, ea.dlogits_cols = dlg.data_ptr(), 1, Kp, Kp
         ea.prior_means, ea.prior_log_vars = pm.data_ptr(), pl.data_ptr()
