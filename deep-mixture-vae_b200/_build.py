@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdmvae_b200.so")
 SOURCES = ["abi.cu", "elbo.cu", "reparam.cu", "gemm_f32.cu", "gemm_tc.cu", "gemm_chain.cu", "moe.cu"]
-HEADERS = ["common.cuh", "epilogue.cuh", "tc_device.cuh", "philox.cuh", os.path.join("..", "..", "include", "dmvae_b200.h")]
+HEADERS = ["common.cuh", "epilogue.cuh", "tc_device.cuh", "philox.cuh", "elbo_mma.cuh", os.path.join("..", "..", "include", "dmvae_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--expt-relaxed-constexpr",
          "-Xcompiler", "-fPIC", "-Xptxas", "-v"]

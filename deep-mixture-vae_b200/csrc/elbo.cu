@@ -1089,9 +1089,12 @@ int launch_elbo_k(dmvae_ctx* ctx, const ElboParams& p, cudaStream_t st) {
   return DMVAE_OK;
 }
 
+#include "elbo_mma.cuh"
+
 template <typename TX, typename TD, int INPUT>
 int launch_elbo(dmvae_ctx* ctx, const ElboParams& p, cudaStream_t st) {
   if (elbo_rowtile_ok(p)) return launch_elbo_rowtile<TX, TD, INPUT>(ctx, p, st);
+  if (elbo_mma_ok(p)) return launch_elbo_mma<TX, TD, INPUT>(ctx, p, st);
   if (p.a.K <= 32) return launch_elbo_k<TX, TD, INPUT, 1>(ctx, p, st);
   if (p.a.K <= 64) return launch_elbo_k<TX, TD, INPUT, 2>(ctx, p, st);
   return launch_elbo_k<TX, TD, INPUT, 4>(ctx, p, st);
@@ -1138,7 +1141,8 @@ extern "C" int dmvae_elbo_fwd_bwd(dmvae_ctx* ctx, const dmvae_elbo_args* a, void
               (a->ddec_cols * ds) % 16 == 0 && (a->ld_ddec * ds) % 16 == 0 && ((uintptr_t)a->X & 15) == 0 &&
               ((uintptr_t)a->decoded & 15) == 0 && ((uintptr_t)a->d_decoded & 15) == 0 && a->ddec_cols >= a->D;
   p.contig = (int64_t)(a->ldx * xs) == p.xrow && (int64_t)(a->ld_dec * ds) == p.drow && (int64_t)(a->ld_ddec * ds) == p.drow;
-  DMVAE_CHECK_ARG(elbo_smem_bytes(a->L, a->K, p.Ls) <= 220 * 1024, "elbo: K*L = %d too large for the shared prior tables", a->K * a->L);
+  DMVAE_CHECK_ARG(elbo_mma_ok(p) || elbo_smem_bytes(a->L, a->K, p.Ls) <= 220 * 1024,
+                  "elbo: K*L = %d too large for the shared prior tables", a->K * a->L);
   cudaStream_t st = (cudaStream_t)stream;
 #define GO(TX, TD)                                                                            \
   return a->input_type == DMVAE_INPUT_BINARY ? launch_elbo<TX, TD, DMVAE_INPUT_BINARY>(ctx, p, st) \
@@ -1246,35 +1250,54 @@ __global__ void __launch_bounds__(kRedThreads) elbo_reduce_final_kernel(const dm
   const int nsets = (a.mode == DMVAE_MODE_VADE) ? 2 : 1;
   const size_t set_stride = (size_t)G * (size_t)(K * nF);
   const float s = a.inv_global_batch, r = a.kl_ratio_dev ? __ldg(a.kl_ratio_dev) : a.kl_ratio;
-  int i = blockIdx.x * kRedThreads + threadIdx.x;
-  if (i < K * L && d_means && d_log_vars) {
-    int k = i / L, l = i - k * L;
+  // A block owns 32 table elements: warp `sub` sums the chunk partials g = sub, sub + 8, ... for them (coalesced rows of
+  // the workspace), the eight warps' sums meet in shared memory and are added in a fixed order (deterministic).
+  __shared__ float part[8][6][32];
+  const int sub = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i = blockIdx.x * 32 + lane;
+  const bool active = i < K * L && d_means && d_log_vars;
+  {
+    const int ii = active ? i : 0;
+    const int k = ii / L, l = ii - k * L;
     float U0 = 0.f, U1 = 0.f, Wk = 0.f, V0 = 0.f, V1 = 0.f, Dk = 0.f;
-#pragma unroll 8
-    for (int g = 0; g < G; ++g) {
-      const float* p0 = ws + (size_t)g * (K * nF) + (size_t)k * nF;
-      U0 += p0[l]; U1 += p0[L + l]; Wk += p0[2 * L];
-      if (nsets == 2) {
-        const float* p1 = p0 + set_stride;
-        V0 += p1[l]; V1 += p1[L + l]; Dk += p1[2 * L];
+    if (active) {
+#pragma unroll 4
+      for (int g = sub; g < G; g += 8) {
+        const float* p0 = ws + (size_t)g * (K * nF) + (size_t)k * nF;
+        U0 += p0[l]; U1 += p0[L + l]; Wk += p0[2 * L];
+        if (nsets == 2) {
+          const float* p1 = p0 + set_stride;
+          V0 += p1[l]; V1 += p1[L + l]; Dk += p1[2 * L];
+        }
       }
     }
-    const float m = a.prior_means[i], plv = a.prior_log_vars[i];
-    float dm, dp;
-    if (a.mode == DMVAE_MODE_DMVAE_SAMPLED) {
-      dm = s * r * U0;
-      dp = s * r * U1;
-    } else {
-      const float iv = expf(-plv);
-      dm = -s * r * iv * (U0 - m * Wk);
-      dp = 0.5f * s * r * (Wk - iv * (U1 - 2.f * m * U0 + m * m * Wk));
-      if (nsets == 2) {
-        dm += iv * (V0 - m * Dk);
-        dp += 0.5f * iv * (V1 - 2.f * m * V0 + m * m * Dk) - 0.5f * Dk;
+    part[sub][0][lane] = U0; part[sub][1][lane] = U1; part[sub][2][lane] = Wk;
+    part[sub][3][lane] = V0; part[sub][4][lane] = V1; part[sub][5][lane] = Dk;
+    __syncthreads();
+    if (active && sub == 0) {
+      U0 = U1 = Wk = V0 = V1 = Dk = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) {
+        U0 += part[w][0][lane]; U1 += part[w][1][lane]; Wk += part[w][2][lane];
+        V0 += part[w][3][lane]; V1 += part[w][4][lane]; Dk += part[w][5][lane];
       }
+      const float m = a.prior_means[i], plv = a.prior_log_vars[i];
+      float dm, dp;
+      if (a.mode == DMVAE_MODE_DMVAE_SAMPLED) {
+        dm = s * r * U0;
+        dp = s * r * U1;
+      } else {
+        const float iv = expf(-plv);
+        dm = -s * r * iv * (U0 - m * Wk);
+        dp = 0.5f * s * r * (Wk - iv * (U1 - 2.f * m * U0 + m * m * Wk));
+        if (nsets == 2) {
+          dm += iv * (V0 - m * Dk);
+          dp += 0.5f * iv * (V1 - 2.f * m * V0 + m * m * Dk) - 0.5f * Dk;
+        }
+      }
+      if (accumulate) { d_means[i] += dm; d_log_vars[i] += dp; }
+      else { d_means[i] = dm; d_log_vars[i] = dp; }
     }
-    if (accumulate) { d_means[i] += dm; d_log_vars[i] += dp; }
-    else { d_means[i] = dm; d_log_vars[i] = dp; }
   }
   if (blockIdx.x == 0 && threadIdx.x < 4 && loss_out) {
     const float* lp = ws + (size_t)nsets * set_stride;
@@ -1289,6 +1312,7 @@ __global__ void __launch_bounds__(kRedThreads) elbo_reduce_final_kernel(const dm
 
 extern "C" int64_t dmvae_elbo_reduce_workspace(int rows, int L, int K) {
   if (rows <= 0 || L <= 0 || K <= 0) return 0;
+  // sized for the smaller of the two chunk sizes in use (scalar kernel: reduce_chunk <= 64; MMA kernel: 64)
   int chunk = reduce_chunk(L, K);
   int64_t G = (rows + chunk - 1) / chunk;
   return 2 * G * (int64_t)K * (2 * L + 1) + 4 * G;
@@ -1302,16 +1326,23 @@ extern "C" int dmvae_elbo_reduce(dmvae_ctx* ctx, const dmvae_elbo_args* a, float
   DMVAE_CHECK_ARG(workspace != nullptr, "elbo_reduce: workspace is NULL");
   DMVAE_CHECK_ARG((d_prior_means == nullptr) == (d_prior_log_vars == nullptr), "elbo_reduce: pass both prior gradients or neither");
   if (a->rows == 0) return DMVAE_OK;
-  const int chunk = reduce_chunk(a->L, a->K);
-  const int G = (a->rows + chunk - 1) / chunk;
   const int nsets = (a->mode == DMVAE_MODE_VADE) ? 2 : 1;
-  const size_t smem = sizeof(float) * (size_t)chunk * (size_t)(a->K + 2 * a->L + 1);
-  if (smem > 48 * 1024)
-    DMVAE_CUDA(cudaFuncSetAttribute(elbo_reduce_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaStream_t st = (cudaStream_t)stream;
-  dmvae_launch(elbo_reduce_partial_kernel, dim3(G, nsets), dim3(kRedThreads), smem, st, true, *a, chunk, G, workspace);
-  DMVAE_LAUNCH_CHECK(ctx);
-  const int fin_blocks = max(1, (a->K * a->L + kRedThreads - 1) / kRedThreads);
+  int G;
+  if (elbo_reduce_mma_ok(*a)) {
+    G = (a->rows + kRedChunkM - 1) / kRedChunkM;
+    rc = launch_elbo_reduce_mma(ctx, *a, G, nsets, workspace, st);
+    if (rc) return rc;
+  } else {
+    const int chunk = reduce_chunk(a->L, a->K);
+    G = (a->rows + chunk - 1) / chunk;
+    const size_t smem = sizeof(float) * (size_t)chunk * (size_t)(a->K + 2 * a->L + 1);
+    if (smem > 48 * 1024)
+      DMVAE_CUDA(cudaFuncSetAttribute(elbo_reduce_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dmvae_launch(elbo_reduce_partial_kernel, dim3(G, nsets), dim3(kRedThreads), smem, st, true, *a, chunk, G, workspace);
+    DMVAE_LAUNCH_CHECK(ctx);
+  }
+  const int fin_blocks = max(1, (a->K * a->L + 31) / 32);
   dmvae_launch(elbo_reduce_final_kernel, dim3(fin_blocks), dim3(kRedThreads), 0, st, true, *a, G, workspace, d_prior_means, d_prior_log_vars,
                                                               accumulate, loss_out);
   DMVAE_LAUNCH_CHECK(ctx);

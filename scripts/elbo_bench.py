@@ -83,7 +83,25 @@ def time_elbo(lib, ctx, B, D=784, L=10, K=10, iters=20, check=False, log=print):
     g.replay()
     e1.record()
     torch.cuda.synchronize()
-    return e0.elapsed_time(e1) * 1e3 / iters, nbuf
+    us = e0.elapsed_time(e1) * 1e3 / iters
+    # the cross-sample reduction of the same pass (prior-table gradients + loss terms), timed the same way
+    gm, gl, lo = torch.zeros(K, L, device="cuda"), torch.zeros(K, L, device="cuda"), torch.zeros(4, device="cuda")
+    ws = torch.zeros(int(lib.dmvae_elbo_reduce_workspace(B, L, K)), device="cuda")
+    red = lambda: _abi.check(lib.dmvae_elbo_reduce(ctx, C.byref(eas[0]), gm.data_ptr(), gl.data_ptr(), 0, lo.data_ptr(), ws.data_ptr(), st()))
+    red()
+    torch.cuda.synchronize()
+    g2 = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g2):
+        for i in range(iters):
+            red()
+    g2.replay()
+    torch.cuda.synchronize()
+    e0.record()
+    g2.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    log("  elbo_reduce (2 kernels) rows %d L %d K %d: %.2f us" % (B, L, K, e0.elapsed_time(e1) * 1e3 / iters))
+    return us, nbuf
 
 
 def elbo_bytes_per_sample(D, L, K):
