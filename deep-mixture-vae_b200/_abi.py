@@ -45,7 +45,8 @@ class ReparamArgs(C.Structure):
                 ("seed", c_uint64), ("step", c_uint64), ("row_offset", c_uint64), ("step_dev", c_void_p),
                 ("tau", c_float),
                 ("Z_out", c_void_p), ("z_dtype", c_int32), ("ld_z", c_int64), ("z_cols", c_int32),
-                ("eps_out", c_void_p), ("zeta_out", c_void_p)]
+                ("eps_out", c_void_p), ("zeta_out", c_void_p),
+                ("fold", c_void_p), ("ld_fold", c_int64), ("fold_K", c_int32), ("fold_stride", c_int32)]
 
 
 class ElboArgs(C.Structure):
@@ -124,6 +125,8 @@ SIGNATURES = {
     "dmvae_dp_barrier": (c_int, [c_void_p, c_int, c_int, C.POINTER(c_void_p), c_void_p, c_int, c_void_p]),
     "dmvae_zero_f32": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "dmvae_cast_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "dmvae_split3_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_void_p]),
+    "dmvae_fold3": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p]),
 }
 
 

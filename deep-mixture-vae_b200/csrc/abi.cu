@@ -108,6 +108,61 @@ extern "C" int dmvae_cast_bf16(dmvae_ctx* ctx, const float* src, void* dst, int6
 }
 
 // ---------------------------------------------------------------------------------------------
+// split-weight logits layer: W = hi + lo + lo2 in three column groups of the bf16 operand copy, and the fold of the
+// three partial products (see include/dmvae_b200.h)
+// ---------------------------------------------------------------------------------------------
+__global__ void split3_bf16_kernel(const float* __restrict__ W, __nv_bfloat16* __restrict__ op, int rows, int64_t ld, int K,
+                                   int stride) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int n = rows * K;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int r = i / K, k = i - r * K;
+    const float w = W[(int64_t)r * ld + k];
+    const __nv_bfloat16 hi = __float2bfloat16_rn(w);
+    const float r1 = w - __bfloat162float(hi);                  // exact (Sterbenz-like: hi is w rounded to 8 bits)
+    const __nv_bfloat16 lo = __float2bfloat16_rn(r1);
+    const float r2 = r1 - __bfloat162float(lo);                 // exact; fits 8 bits
+    __nv_bfloat16* o = op + (int64_t)r * ld + k;
+    o[0] = hi;
+    o[stride] = lo;
+    o[2 * stride] = __float2bfloat16_rn(r2);
+  }
+}
+
+extern "C" int dmvae_split3_bf16(dmvae_ctx* ctx, const float* W, void* W_bf16, int rows, int64_t ld, int K, int stride,
+                                 void* stream) {
+  DMVAE_CHECK_ARG(ctx && W && W_bf16 && rows >= 0 && K > 0 && stride >= K && ld >= 2 * (int64_t)stride + K,
+                  "split3_bf16: need K <= stride and 2 stride + K <= ld");
+  if (rows == 0) return DMVAE_OK;
+  const int blocks = min(ctx->sm_count * 4, (rows * K + 255) / 256);
+  dmvae_launch(split3_bf16_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, true, W, (__nv_bfloat16*)W_bf16, rows, ld, K, stride);
+  DMVAE_LAUNCH_CHECK(ctx);
+  return DMVAE_OK;
+}
+
+__global__ void fold3_kernel(float* __restrict__ Y, int64_t ld, int rows, int K, int stride) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int n = rows * K;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int r = i / K, k = i - r * K;
+    float* y = Y + (int64_t)r * ld + k;
+    y[0] = (y[2 * stride] + y[stride]) + y[0];                  // smallest terms first
+  }
+}
+
+extern "C" int dmvae_fold3(dmvae_ctx* ctx, float* Y, int64_t ld, int rows, int K, int stride, void* stream) {
+  DMVAE_CHECK_ARG(ctx && Y && rows >= 0 && K > 0 && stride >= K && ld >= 2 * (int64_t)stride + K,
+                  "fold3: need K <= stride and 2 stride + K <= ld");
+  if (rows == 0) return DMVAE_OK;
+  const int blocks = min(ctx->sm_count * 4, (rows * K + 255) / 256);
+  dmvae_launch(fold3_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, true, Y, ld, rows, K, stride);
+  DMVAE_LAUNCH_CHECK(ctx);
+  return DMVAE_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // input staging: X -> operand matrix with the ones column
 // ---------------------------------------------------------------------------------------------
 template <typename TX, typename TO>

@@ -22,6 +22,11 @@ __global__ void __launch_bounds__(256) reparam_fwd_kernel(const dmvae_reparam_ar
     const float* mean = a.mean + (int64_t)row * a.ld_zh;
     const float* lv = a.log_var + (int64_t)row * a.ld_zh;
     TZ* z = reinterpret_cast<TZ*>(a.Z_out) + (int64_t)row * a.ld_z;
+    if (a.fold) {                              // split-weight logits: hi + lo + lo2 partial products (dmvae_split3_bf16)
+      float* y = a.fold + (int64_t)row * a.ld_fold;
+      for (int k = lane; k < a.fold_K; k += 32) y[k] = (y[2 * a.fold_stride + k] + y[a.fold_stride + k]) + y[k];
+      __syncwarp();
+    }
     // ---- Gaussian part: one Philox block covers 4 columns ----
     for (int j = lane; j * 4 < L; j += 32) {
       float e[4];
@@ -118,6 +123,8 @@ extern "C" int dmvae_reparam_fwd(dmvae_ctx* ctx, const dmvae_reparam_args* a, vo
   DMVAE_CHECK_ARG(a->mean && a->log_var && a->Z_out && a->eps_out, "reparam_fwd: mean, log_var, Z_out, eps_out required");  // priors.py:87
   DMVAE_CHECK_ARG(a->z_cols <= a->ld_z && a->ld_z >= a->L, "reparam_fwd: ld_z too small");
   if (a->zeta_out) DMVAE_CHECK_ARG(a->logits && a->tau > 0.f, "reparam_fwd: the concrete sample needs logits and temperature > 0");  // priors.py:171
+  if (a->fold) DMVAE_CHECK_ARG(a->fold_K > 0 && a->fold_stride >= a->fold_K && a->ld_fold >= 2 * (int64_t)a->fold_stride + a->fold_K,
+                               "reparam_fwd: fold needs K <= stride and 2 stride + K <= ld");
   if (a->rows == 0) return DMVAE_OK;
   int blocks = min(ctx->sm_count * 8, (a->rows + 7) / 8);
   cudaStream_t st = (cudaStream_t)stream;

@@ -233,11 +233,21 @@ class DataParallel:
             if e <= b:
                 continue
             m, v = self._opt_shard_state(opt, ridx)
-            # The prior tables (the tail of the flat buffer) are read in fp32 by the fused ELBO kernel on EVERY rank
-            # (Engine._elbo_args), so their fp32 master must stay replicated even when the rest of the master is kept by
-            # its owner only: the part of the shard that overlaps them is exchanged with all fp32 peer pointers set.
-            t0 = eng.off_means if self.master_sharded else e
-            pieces = [(b, min(e, t0), False), (max(b, t0), e, True)]
+            # Some ranges need their fp32 master on EVERY rank even when the rest of the master is kept by its owner only
+            # (Layout.replicated_master_ranges: the prior tables, read in fp32 by the fused ELBO kernel, and the logits
+            # layer, whose split bf16 operand copy is rebuilt from the master): the parts of the shard that overlap them
+            # are exchanged with all fp32 peer pointers set.
+            pieces, pos = [], b
+            for lo, hi in (eng.layout.replicated_master_ranges() if self.master_sharded else []):
+                lo, hi = max(lo, b), min(hi, e)
+                if hi <= lo:
+                    continue
+                if lo > pos:
+                    pieces.append((pos, lo, False))
+                pieces.append((lo, hi, True))
+                pos = hi
+            if pos < e:
+                pieces.append((pos, e, False))
             for pb, pe, full in pieces:
                 if pe <= pb:
                     continue
@@ -255,6 +265,7 @@ class DataParallel:
                                                        eng.n_params, pb, pe, lr_t, lr_dev, opt.beta1, opt.beta2, opt.eps,
                                                        2 if background else 0, eng._stream()))
         self._barrier(ch + 1)                             # every replica updated, every gradient shard consumed
+        eng._refresh_split_heads()                        # logits layer: hi | lo | lo2 operand copy from the (replicated) master
         # clear the local gradients of these ranges (split-K accumulates into them): local HBM, not 7/8 remote stores
         if self.defer_clear:
             return
@@ -304,6 +315,7 @@ class DataParallel:
             abi.check(eng.lib.dmvae_adam(eng.ctx, eng.params.data_ptr(), eng.grads.data_ptr(), opt.m.data_ptr(),
                                          opt.v.data_ptr(), eng.params_op.data_ptr() if eng.params_op is not None else None,
                                          eng.n_params, lr_t, lr_dev, opt.beta1, opt.beta2, opt.eps, 1.0, 1, eng._stream()))
+            eng._refresh_split_heads()
         eng._grads_dirty = False
 
     def mark_updated(self):

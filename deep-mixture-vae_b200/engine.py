@@ -68,6 +68,7 @@ class Layout:
             raise NotImplementedError(model)
         self.model, self.name = model, name
         self.D, self.L, self.K = input_dim, latent_dim, n_classes
+        self.Kc = ((n_classes + 7) // 8) * 8
         self.trunk, self.head, self.decoder, self.moe = tuple(trunk), head, tuple(decoder), moe
         self._build_layers()
         off = 0
@@ -125,6 +126,16 @@ class Layout:
             out.append((pos, self.n_params))
         return out
 
+    def replicated_master_ranges(self) -> List[Tuple[int, int]]:
+        """[lo, hi) ranges of the flat buffer whose fp32 master every data-parallel rank needs locally: the prior tables
+        (read by the fused ELBO kernel) and the logits layer (its split bf16 operand copy is rebuilt from the master)."""
+        rs = []
+        if "ch" in self.layers:
+            ly = self.layers["ch"]
+            rs.append((ly.offset, ly.offset + ly.size))
+        rs.append((self.off_means, self.n_params))
+        return rs
+
     def reference_parameter_count(self) -> int:
         """Number of reference parameters that receive a gradient (4 373 014 for cfg1/2)."""
         return int(sum(int(np.prod(v.shape)) for v in self.vars.values()))
@@ -156,7 +167,10 @@ class Layout:
             add("zh", hh, round64(2 * L), 1, 1)                           # [mean | log_var], fp32 out
             dense_vars("zh", e + "/z/dense_1/kernel", e + "/z/dense_1/bias", hh, 0, L, (L,), "zeros")
             dense_vars("zh", e + "/z/dense_2/kernel", e + "/z/dense_2/bias", hh, L, L, (L,), "zeros")
-            add("ch", hh, round64(K), 1, 1)                               # logits, fp32 out
+            # logits, fp32 out.  Three column groups of stride Kc: the bf16 operand copy carries W = hi + lo + lo2 there
+            # (dmvae_split3_bf16) so that the bf16 tier's logits are fp32-exact; the fp32 master has K valid columns
+            self.Kc = ((K + 7) // 8) * 8
+            add("ch", hh, round64(3 * self.Kc), 1, 1)
             dense_vars("ch", e + "/c/dense_1/kernel", e + "/c/dense_1/bias", hh, 0, K, (K,), "zeros")
             self.enc_chain = ["enc1", "enc2"]
             self.last_hidden = h2
@@ -255,6 +269,8 @@ class Engine:
         if self.dt == F32:
             self.dec_dt = F32
         self.moe = moe
+        # exact cluster assignments in the bf16 tier: split-weight logits layer (include/dmvae_b200.h, dmvae_split3_bf16)
+        self.split_heads = (self.dt == BF16 and model == "dmvae" and os.environ.get("DMVAE_SPLIT_HEADS", "1") != "0")
         self.seed = seed
         self.noise_seed = seed + 2
         self.step_count = 0
@@ -273,7 +289,7 @@ class Engine:
         self.layout = Layout(model=model, input_dim=input_dim, latent_dim=latent_dim, n_classes=n_classes, trunk=trunk,
                              head=head, decoder=decoder, name=name, moe=moe)
         for k in ("layers", "vars", "enc_chain", "dec_chain", "dead_vars", "last_hidden", "tab_size", "off_means",
-                  "off_log_vars", "n_params"):
+                  "off_log_vars", "n_params", "Kc"):
             setattr(self, k, getattr(self.layout, k))
         self._alloc_params()
         self.max_rows = 0
@@ -394,7 +410,24 @@ class Engine:
         if self.params_op is not None:
             _abi.check(self.lib.dmvae_cast_bf16(self.ctx, self.params.data_ptr(), self.params_op.data_ptr(),
                                                 self.n_params, self._stream()))
+            self._refresh_split_heads()
         self._params_dirty = False
+
+    def _refresh_split_heads(self) -> None:
+        """Rebuild the three-group bf16 operand copy (hi | lo | lo2) of the logits layer from its fp32 master; called
+        after every rewrite of that block's operand copy (load, Adam, data-parallel exchange)."""
+        if not self.split_heads:
+            return
+        ly = self.layers["ch"]
+        _abi.check(self.lib.dmvae_split3_bf16(self.ctx, self.params.data_ptr() + 4 * ly.offset,
+                                              self.params_op.data_ptr() + 2 * ly.offset, ly.in_pad, ly.out_pad, self.K,
+                                              self.Kc, self._stream()))
+
+    def _fold_logits(self, rows: int) -> None:
+        """logits = hi + lo + lo2 partial products of the split-weight GEMM (when reparam() is not the one folding)."""
+        if self.split_heads:
+            _abi.check(self.lib.dmvae_fold3(self.ctx, self.ch.data_ptr(), self.ch.stride(0), rows, self.K, self.Kc,
+                                            self._stream()))
 
     # ------------------------------------------------------------------------------------------
     # activations
@@ -682,8 +715,19 @@ class Engine:
     # ------------------------------------------------------------------------------------------
     # forward
     # ------------------------------------------------------------------------------------------
-    def encode(self, rows: int, heads=("z", "c")):
-        """Encoder trunk and heads (base_models.py:218-249 / :490-513)."""
+    def encode(self, rows: int, heads=("z", "c"), fold_in_reparam: bool = False):
+        """Encoder trunk and heads (base_models.py:218-249 / :490-513).  fold_in_reparam: the caller runs reparam() next,
+        which folds the split-weight logits itself (one launch fewer on the step's critical path)."""
+        self._logits_unfolded = False
+        self._encode(rows, heads)
+        if self.model == "dmvae" and "c" in heads and self.split_heads:
+            if fold_in_reparam:
+                self._logits_unfolded = True
+            else:
+                self._join()
+                self._fold_logits(rows)
+
+    def _encode(self, rows: int, heads):
         a = self.act["x"]
         # A narrow head (N = 64) over a deep reduction is bound by what ONE SM can pull from L2 (~65 GB/s measured:
         # 32 CTAs took 12 us); split-K spreads the same bytes over 4x the SMs.  The partial sums reduce into fp32
@@ -746,6 +790,10 @@ class Engine:
         ra.Z_out, ra.z_dtype, ra.ld_z, ra.z_cols = self.zb.data_ptr(), self.dt, self.zb.stride(0), self.zb.shape[1]
         ra.eps_out = self.eps.data_ptr()
         ra.zeta_out = self.zeta.data_ptr() if want_zeta else None
+        if getattr(self, "_logits_unfolded", False):
+            self._join()
+            ra.fold, ra.ld_fold, ra.fold_K, ra.fold_stride = self.ch.data_ptr(), self.ch.stride(0), self.K, self.Kc
+            self._logits_unfolded = False
         _abi.check(self.lib.dmvae_reparam_fwd(self.ctx, C.byref(ra), self._stream()))
 
     def decode(self, rows: int):
@@ -765,7 +813,7 @@ class Engine:
     use_chain = os.environ.get("DMVAE_CHAIN", "0") == "1"
 
     def _chain_ok(self, gumbel_injected: bool) -> bool:
-        return (self.use_chain and self.dt == BF16 and self.timers is None and 2 * self.L <= 32
+        return (self.use_chain and not self.split_heads and self.dt == BF16 and self.timers is None and 2 * self.L <= 32
                 and not (self.model == "dmvae" and self.cluster_sample) and not gumbel_injected)
 
     def _chain_entry(self, name, A, lda, C, ldc, out_dt, act, rows, dep=-1, fuse=0, n=None, k=None, W=None, ldw=None):
@@ -1009,6 +1057,7 @@ class Engine:
                                        self.n_params, lr_t, (opt.state_dev.data_ptr() + 12) if use_dev else None,
                                        opt.beta1, opt.beta2, opt.eps, 1.0, 1 if zero_grads else 0, self._stream()))
         self._toc("adam", t0)
+        self._refresh_split_heads()
         if zero_grads:
             self._grads_dirty = False
 
@@ -1061,6 +1110,8 @@ class Engine:
                 return
             for off, n in merged:
                 self._adam_range(opt, off, n, background=self.dt == BF16)
+            if "ch" in names:
+                self._refresh_split_heads()
 
         self._fork(run)
         done.extend(merged)
@@ -1073,9 +1124,12 @@ class Engine:
             self.dp.update(opt, True, skip=done)
             return
         pos = 0
+        ch = self.layers.get("ch")
         for off, n in done + [(self.n_params, 0)]:
             if off > pos:
                 self._adam_range(opt, pos, off - pos)
+                if ch is not None and pos <= ch.offset < off:
+                    self._refresh_split_heads()
             pos = max(pos, off + n)
         self._grads_dirty = False
 
@@ -1104,7 +1158,7 @@ class Engine:
         if self._chain_ok(gumbel is not None):
             self.forward_chain(rows, eps is not None, row_offset, step_dev=sdev)
         else:
-            self.encode(rows)
+            self.encode(rows, fold_in_reparam=True)
             self.reparam(rows, eps is not None, gumbel is not None, row_offset, step_dev=sdev)
             self.decode(rows)
         flags = dict(all=(True, True, True, True), vae=(True, True, False, True), prior=(False, False, True, False))[mode]
@@ -1142,7 +1196,7 @@ class Engine:
         Xs, xdt = self.stage_input(X, rows)
         full = lossVAE or self.model == "vade"
         if full:
-            self.encode(rows)
+            self.encode(rows, fold_in_reparam=True)
             self.reparam(rows, eps is not None, gumbel is not None)
             self.decode(rows)
             self.elbo(Xs, xdt, rows, kl_ratio if lossVAE else 0.0, None, 1.0 if lossVAE else 0.0, prior_grads=lossVAE)

@@ -119,6 +119,9 @@ typedef struct dmvae_reparam_args {
   void* Z_out; int32_t z_dtype; int64_t ld_z; int32_t z_cols; /* Z in operand dtype, [rows, ld_z]; ones column at L, zeros to z_cols */
   float* eps_out;                                             /* fp32 [rows, L]: the eps actually used (kept for the backward) */
   float* zeta_out;                                            /* fp32 [rows, K] or NULL */
+  /* optional: fold the three column groups of a split-weight logits GEMM first (see dmvae_split3_bf16):
+   * fold[r, k] += fold[r, stride + k] + fold[r, 2 stride + k], k < fold_K.  `logits` may alias `fold`. */
+  float* fold; int64_t ld_fold; int32_t fold_K; int32_t fold_stride;
 } dmvae_reparam_args;
 int dmvae_reparam_fwd(dmvae_ctx* ctx, const dmvae_reparam_args* a, void* stream);
 
@@ -279,6 +282,16 @@ int dmvae_dp_barrier(dmvae_ctx* ctx, int rank, int world, uint32_t* const* pads_
 int dmvae_zero_f32(dmvae_ctx* ctx, float* p, int64_t n, void* stream);
 /* fp32 -> bf16 copy (operand copy of the parameters) */
 int dmvae_cast_bf16(dmvae_ctx* ctx, const float* src, void* dst, int64_t n, void* stream);
+
+/* ---- exact cluster assignments with bf16 tensor cores (base_models.py:241-249, :425-432) -------------------------
+ * The logits layer has K <= stride valid output columns inside a zero-padded block of >= 3 stride columns.  Its bf16
+ * OPERAND copy is written as three column groups  W = hi + lo + lo2  (8 + 8 + 8 mantissa bits: the fp32 weight exactly):
+ *   op[r, k] = bf16(W[r,k]),  op[r, stride+k] = bf16(W - hi),  op[r, 2 stride+k] = bf16(W - hi - lo),   k < K,
+ * so ONE tcgen05 GEMM of unchanged shape yields three partial logits whose sum (dmvae_fold3, or the fold of
+ * dmvae_reparam_fwd) is the fp32-exact product of the bf16 activations with the fp32 weights: argmax q(c|x) no longer
+ * depends on the rounding of the weights.  The padding columns carry zero gradients, so dgrad / wgrad are unaffected. */
+int dmvae_split3_bf16(dmvae_ctx* ctx, const float* W, void* W_bf16, int rows, int64_t ld, int K, int stride, void* stream);
+int dmvae_fold3(dmvae_ctx* ctx, float* Y, int64_t ld, int rows, int K, int stride, void* stream);
 
 #ifdef __cplusplus
 }

@@ -250,8 +250,11 @@ def test_elbo_dmvae_fp32(lib, ctx, B, D, L, K, binary):
     assert np.all(got["d_logits"][:, K:] == 0)
 
 
-def test_elbo_u8_and_bf16_variants(lib, ctx):
-    B, D, L, K = 256, 784, 10, 10
+@pytest.mark.parametrize("B", [256, 17, 4095, 1])
+def test_elbo_u8_and_bf16_variants(lib, ctx, B):
+    """uint8 targets and the bf16 tier of the row-tile kernel (the benchmarked variant), including ragged row counts:
+    17 = one full 16-row tile + a 1-row tile, 4095 = the last tile one row short."""
+    D, L, K = 784, 10, 10
     X, dec, mean, lv, logits, eps, m, plv = _elbo_inputs(B, D, L, K, 1, True)
     c = cf.elbo_dmvae(*[a.astype(np.float64) for a in (X, dec, mean, lv, logits, m, plv)])
     got = _run_elbo(lib, ctx, 0, 0, X, dec, mean, lv, logits, None, None, 1.0, m, plv, 1.0, 1.0 / B, x_dtype=2)
@@ -260,8 +263,10 @@ def test_elbo_u8_and_bf16_variants(lib, ctx):
     cb = cf.elbo_dmvae(*[a.astype(np.float64) for a in (X, decb, mean, lv, logits, m, plv)])
     got = _run_elbo(lib, ctx, 0, 0, X, dec, mean, lv, logits, None, None, 1.0, m, plv, 1.0, 1.0 / B, x_dtype=2, dec_dtype=1)
     ref_ps = np.stack([cb["R"], cb["C"], cb["Zk"], cb["elbo"]], 1)
-    # bf16 tier (north_star tolerance 2e-2): the reconstruction term is evaluated in packed half2 arithmetic;
-    # measured error is ~1e-4, asserted at 1e-3.  The latent terms stay fp32 (1e-4).
+    # bf16 tier (north_star tolerance 2e-2): the reconstruction term uses the one-MUFU tanh formulation in fp32;
+    # measured error is ~1e-5, asserted at 1e-3.  The latent terms stay fp32 (1e-4).
+    assert np.array_equal(got["argmax"], cb["argmax"])
+    assert np.all(got["d_decoded"][:, D:] == 0) and np.all(got["d_logits"][:, K:] == 0)
     assert np.all(np.abs(got["per_sample"][:, 1:3] - ref_ps[:, 1:3]) <= 1e-4 * np.abs(ref_ps[:, 1:3]) + 2e-5)
     assert np.all(np.abs(got["per_sample"] - ref_ps) <= 1e-3 * np.abs(ref_ps) + 2e-5)
     assert relerr(got["d_decoded"][:, :D], cb["d_decoded"]) < 1e-2          # bf16 store
@@ -297,8 +302,12 @@ def test_elbo_rejects_bad_input_type(lib, ctx):
     from dmvae_b200 import _abi
     ea = _abi.ElboArgs()
     ea.input_type = 5
-    assert lib.dmvae_elbo_fwd_bwd(ctx, C.byref(ea), stream()) != 0
-    assert b"not implemented" in lib.dmvae_last_error() or b"NULL" in lib.dmvae_last_error() or True
+    ea.mode, ea.rows, ea.D, ea.L, ea.K = 0, 4, 8, 2, 2
+    assert lib.dmvae_elbo_fwd_bwd(ctx, C.byref(ea), stream()) == 1            # DMVAE_ERR_INVALID
+    assert b"not implemented" in lib.dmvae_last_error()                       # base_models.py:84-85
+    ea.input_type = 0
+    assert lib.dmvae_elbo_fwd_bwd(ctx, C.byref(ea), stream()) == 1            # NULL inputs are rejected, not dereferenced
+    assert b"NULL" in lib.dmvae_last_error()
 
 
 # ---------------------------------------------------------------------------------------------

@@ -269,6 +269,8 @@ def test_chained_forward_is_bit_identical_to_layered():
     for model, rows in (("dmvae", 300), ("dmvae", 64), ("vade", 257)):
         cfg, eng, V = _make(model, "bf16")
         eng._head_split_k = lambda rows: 1       # same summation order in both schedules (no k-splits of the heads)
+        eng.split_heads = False                  # the chained forward fuses the reparameterisation into the head's epilogue
+        eng.sync_operand_copy()                  # and has no slot for the split-weight logits fold: plain bf16 weights
         rs = np.random.RandomState(7)
         X = torch.tensor((rs.uniform(size=(rows, cfg.input_dim)) < 0.2).astype(np.float32), device="cuda")
         eps = torch.tensor(rs.randn(rows, cfg.latent_dim).astype(np.float32), device="cuda")
