@@ -236,9 +236,9 @@ class VAE:
         eng = self._ensure_engine(session)
         key, mode = self._TRAIN_OPS[op]
         opt = eng.optimizer(key, self._lr[key])
-        data.begin_epoch()
-        host = data.host_tensor()
-        return eng.run_epoch(host, data.batch_size, opt, kl_ratio, mode)
+        data.begin_epoch()                                     # draws the epoch's permutation (utils.py:450-454)
+        runner = eng.dp if eng.dp is not None else eng
+        return runner.run_epoch(data.host_tensor(), data.batch_size, opt, kl_ratio, mode, perm=data.perm)
 
     def debug(self, session, data):
         """base_models.py:134-147 drops into pdb; here the prepared feed is returned instead."""
@@ -358,14 +358,23 @@ class DeepMixtureVAE(VAE):
         n_labels = max(K, int(np.max(data.classes)) + 1)
         counts = torch.zeros(K, n_labels, dtype=torch.int32, device=eng.device)
         total = 0
-        bs = max(data.batch_size, min(eng.max_rows, 4096))
+        bs = max(1, min(eng.max_rows, 4096))                  # chunked to the buffers the engine already has
         classes = torch.from_numpy(np.asarray(data.classes).astype(np.int32)).to(eng.device)
+        # batches come from the dataset's pinned host copy (storage dtype: 1 byte / pixel for binarised data), staged
+        # asynchronously into a persistent device buffer; rows stay in their original order, like data.classes
+        host = data.host_tensor() if isinstance(data, Dataset) else None
+        buf = None
+        if host is not None:
+            buf = getattr(eng, "_eval_stage", None)
+            if buf is None or buf.shape[0] < bs or buf.dtype != host.dtype:
+                buf = eng._eval_stage = torch.empty(bs, eng.D, dtype=host.dtype, device=eng.device)
         for i in range(0, len(data.data), bs):
-            batch = data.data[i:i + bs]
-            rows = len(batch)
-            Xd = _to_device(batch, eng.device, torch.float32)
-            if rows > eng.max_rows:
-                eng._alloc_activations(rows)
+            rows = min(bs, len(data.data) - i)
+            if host is not None:
+                buf[:rows].copy_(host[i:i + rows], non_blocking=True)
+                Xd = buf
+            else:
+                Xd = _to_device(data.data[i:i + rows], eng.device, torch.float32)
             eng.stage_input(Xd, rows)
             eng.encode(rows, heads=("c",))
             _abi.check(eng.lib.dmvae_argmax_contingency(eng.ctx, eng.ch.data_ptr(), eng.ch.stride(0), rows, K,

@@ -220,6 +220,62 @@ extern "C" int dmvae_stage_input(dmvae_ctx* ctx, const void* X, int x_dtype, int
 }
 
 // ---------------------------------------------------------------------------------------------
+// shuffled minibatch gather (source may be pinned host memory: zero-copy reads)
+// ---------------------------------------------------------------------------------------------
+template <typename V>
+__global__ void __launch_bounds__(256) gather_rows_kernel(const uint8_t* __restrict__ src, int64_t src_pitch,
+                                                           const int32_t* __restrict__ idx, uint8_t* __restrict__ dst,
+                                                           int64_t dst_pitch, int rows, int vecs_per_row) {
+  // flat over (row, vector): consecutive threads read consecutive 16-byte (4-byte) pieces of a row; four independent
+  // loads in flight per thread - the reads are bus-latency bound when the source is host memory
+  const int64_t total = (int64_t)rows * vecs_per_row;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + 3 * stride < total; i += 4 * stride) {
+    V v[4];
+    int64_t r[4], c[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int64_t e = i + j * stride;
+      r[j] = e / vecs_per_row;
+      c[j] = e - r[j] * vecs_per_row;
+      v[j] = *reinterpret_cast<const V*>(src + (int64_t)idx[r[j]] * src_pitch + c[j] * (int64_t)sizeof(V));
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) *reinterpret_cast<V*>(dst + r[j] * dst_pitch + c[j] * (int64_t)sizeof(V)) = v[j];
+  }
+  for (; i < total; i += stride) {
+    const int64_t r = i / vecs_per_row, c = i - r * vecs_per_row;
+    *reinterpret_cast<V*>(dst + r * dst_pitch + c * (int64_t)sizeof(V)) =
+        *reinterpret_cast<const V*>(src + (int64_t)idx[r] * src_pitch + c * (int64_t)sizeof(V));
+  }
+}
+
+extern "C" int dmvae_gather_rows(dmvae_ctx* ctx, const void* src, int64_t src_pitch_bytes, const int32_t* idx, void* dst,
+                                 int64_t dst_pitch_bytes, int rows, int row_bytes, void* stream) {
+  DMVAE_CHECK_ARG(ctx && src && idx && dst && rows >= 0 && row_bytes > 0, "gather_rows: bad arguments");
+  DMVAE_CHECK_ARG(src_pitch_bytes >= row_bytes && dst_pitch_bytes >= row_bytes, "gather_rows: pitches smaller than a row");
+  DMVAE_CHECK_ARG(row_bytes % 4 == 0 && src_pitch_bytes % 4 == 0 && dst_pitch_bytes % 4 == 0 &&
+                      ((uintptr_t)src & 3) == 0 && ((uintptr_t)dst & 3) == 0,
+                  "gather_rows: rows and pitches must be multiples of 4 bytes");
+  if (rows == 0) return DMVAE_OK;
+  const bool v16 = row_bytes % 16 == 0 && src_pitch_bytes % 16 == 0 && dst_pitch_bytes % 16 == 0 &&
+                   ((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 15) == 0;
+  const int vpr = row_bytes / (v16 ? 16 : 4);
+  const int64_t total = (int64_t)rows * vpr;
+  const int blocks = (int)min((int64_t)ctx->sm_count * 8, (total + 1023) / 1024);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (v16)
+    gather_rows_kernel<uint4><<<max(1, blocks), 256, 0, st>>>((const uint8_t*)src, src_pitch_bytes, idx, (uint8_t*)dst,
+                                                              dst_pitch_bytes, rows, vpr);
+  else
+    gather_rows_kernel<uint32_t><<<max(1, blocks), 256, 0, st>>>((const uint8_t*)src, src_pitch_bytes, idx, (uint8_t*)dst,
+                                                                 dst_pitch_bytes, rows, vpr);
+  DMVAE_LAUNCH_CHECK(ctx);
+  return DMVAE_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Adam, TensorFlow semantics: theta -= lr_t * m / (sqrt(v) + eps)
 // 16 B read (p,g,m,v) + 12 B written (p,m,v) per parameter (+2 B bf16 copy, +4 B gradient clear).
 // ---------------------------------------------------------------------------------------------

@@ -345,9 +345,9 @@ class DataParallel:
     def train_step(self, X, rows, opt, kl_ratio=1.0):
         self.eng.train_step(X, rows, opt, kl_ratio=kl_ratio)
 
-    def run_epoch(self, host, batch_size, opt, kl_ratio=1.0, max_steps=None):
+    def run_epoch(self, host, batch_size, opt, kl_ratio=1.0, mode="all", max_steps=None, perm=None):
         """Every rank iterates over ITS host shard; the returned loss is the global mean (one all-reduce per epoch)."""
-        loss = self.eng.run_epoch(host, batch_size, opt, kl_ratio, "all", max_steps)
+        loss = self.eng.run_epoch(host, batch_size, opt, kl_ratio, mode, max_steps, perm)
         t = torch.tensor([loss], dtype=torch.float64, device=self.eng.device)
         dist.all_reduce(t, group=self.group)
         return float(t[0])

@@ -720,12 +720,12 @@ class Engine:
         which folds the split-weight logits itself (one launch fewer on the step's critical path)."""
         self._logits_unfolded = False
         self._encode(rows, heads)
-        if self.model == "dmvae" and "c" in heads and self.split_heads:
-            if fold_in_reparam:
-                self._logits_unfolded = True
-            else:
-                self._join()
-                self._fold_logits(rows)
+        if fold_in_reparam:
+            self._logits_unfolded = self.model == "dmvae" and "c" in heads and self.split_heads
+            return                               # reparam() joins the side stream (the c-head may still be running there)
+        self._join()                             # stand-alone use (evaluation, fetches): both heads complete on return
+        if self.model == "dmvae" and "c" in heads:
+            self._fold_logits(rows)
 
     def _encode(self, rows: int, heads):
         a = self.act["x"]
@@ -1176,11 +1176,13 @@ class Engine:
     # mixture-of-experts head (models.py:53-111, :149-163)
     # ------------------------------------------------------------------------------------------
     def moe_step(self, X: torch.Tensor, Y: torch.Tensor, rows: int, opt: Optional[AdamState], eps=None, gumbel=None,
-                 kl_ratio: float = 1.0, train: bool = True):
+                 kl_ratio: float = 1.0, train: bool = True, graph: bool = False):
         """Gate = q(c|x) of the VAE, experts = one dense GEMM over all experts; supervised loss (+ the VAE loss when
-        lossVAE).  Fills moe_loss = [supervised loss, error] and loss_out (VAE terms when lossVAE)."""
-        cfg = self.moe
-        E, O, lossVAE, feat = cfg["n_experts"], cfg["output_dim"], bool(cfg["lossVAE"]), bool(cfg["featLearn"])
+        lossVAE).  Fills moe_loss = [supervised loss, error] and loss_out (VAE terms when lossVAE).
+        graph=True (persistent X / Y buffers, device noise): the step is captured once into a CUDA graph and replayed,
+        with Adam's lr_t and the Philox step read from device memory."""
+        if graph and train and opt is not None and eps is None and gumbel is None and self.use_graphs:
+            return self._moe_step_graph(X, Y, rows, opt, kl_ratio)
         if rows > self.max_rows:
             self._alloc_activations(rows)
         if getattr(self, "_params_dirty", False):
@@ -1191,15 +1193,53 @@ class Engine:
             self.eps_in[:rows].copy_(eps.reshape(rows, self.L))
         if gumbel is not None:
             self.gumbel_in[:rows].copy_(gumbel.reshape(rows, self.K))
+        self._moe_body(X, Y, rows, eps is not None, gumbel is not None, kl_ratio, train, None)
+        if train and opt is not None:
+            self._update(opt)
+            self.step_count += 1
+
+    def _moe_step_graph(self, X, Y, rows, opt, kl_ratio):
+        key = ("moe", X.data_ptr(), X.dtype, Y.data_ptr(), rows, id(opt), float(kl_ratio))
+        ent = self._graphs.get(key)
+        if ent is None:
+            self.moe_step(X, Y, rows, opt, kl_ratio=kl_ratio, graph=False)       # eager: warms descriptor caches
+            torch.cuda.current_stream(self.device).synchronize()
+            g = torch.cuda.CUDAGraph()
+            l0 = int(self.lib.dmvae_ctx_launch_count(self.ctx))
+            with torch.cuda.graph(g):
+                self._fork(lambda: _abi.check(self.lib.dmvae_step_tick(self.ctx, opt.state_dev.data_ptr(), opt.lr,
+                                                                        opt.beta1, opt.beta2, self._stream())))
+                self._moe_body(X, Y, rows, False, False, kl_ratio, True, opt)
+                self._update(opt, use_dev=True)
+            self._graphs[key] = (g, int(self.lib.dmvae_ctx_launch_count(self.ctx)) - l0, False)
+            self._grads_dirty = False
+            return
+        g, n_nodes, _ = ent
+        if getattr(self, "_params_dirty", False):
+            self.sync_operand_copy()
+        if getattr(self, "_grads_dirty", False):
+            self.zero_grads()
+        if not opt.state_valid:
+            opt.upload_state(self.step_count)
+        g.replay()
+        self._grads_dirty = False
+        opt.t += 1
+        self.step_count += 1
+        self._graph_replay_launches += n_nodes
+
+    def _moe_body(self, X, Y, rows, eps_injected, gumbel_injected, kl_ratio, train, dev_state):
+        cfg = self.moe
+        E, O, lossVAE, feat = cfg["n_experts"], cfg["output_dim"], bool(cfg["lossVAE"]), bool(cfg["featLearn"])
+        sdev = dev_state.state_dev.data_ptr() if dev_state is not None else None
         self.y_buf[:rows].copy_(Y.reshape(rows, O))
         st = self._stream
         Xs, xdt = self.stage_input(X, rows)
         full = lossVAE or self.model == "vade"
         if full:
             self.encode(rows, fold_in_reparam=True)
-            self.reparam(rows, eps is not None, gumbel is not None)
+            self.reparam(rows, eps_injected, gumbel_injected, step_dev=sdev)
             self.decode(rows)
-            self.elbo(Xs, xdt, rows, kl_ratio if lossVAE else 0.0, None, 1.0 if lossVAE else 0.0, prior_grads=lossVAE)
+            self.elbo(Xs, xdt, rows, kl_ratio if lossVAE else 0.0, None, 1.0 if lossVAE else 0.0, prior_grads=lossVAE and train)
             self._join()
         else:
             self.encode(rows, heads=("z", "c") if feat else ("c",))
@@ -1255,9 +1295,6 @@ class Engine:
                       through_decoder=lossVAE)
         self._grads_dirty = True
         self._join()
-        if opt is not None:
-            self._update(opt)
-            self.step_count += 1
 
     use_graphs = True
 
@@ -1355,10 +1392,13 @@ class Engine:
         self._graph_replay_launches += n_nodes
 
     def run_epoch(self, host: torch.Tensor, batch_size: int, opt: AdamState, kl_ratio: float = 1.0, mode: str = "all",
-                  max_steps: Optional[int] = None) -> float:
-        """One pass over a (pinned) host array [N, D]: per step an asynchronous host->device copy of the batch on a
-        copy stream (double-buffered, overlapping the previous step), the training step, and an asynchronous read of
-        its loss.  One synchronisation at the end.  Returns the mean batch loss (base_models.py:130)."""
+                  max_steps: Optional[int] = None, perm: Optional[np.ndarray] = None) -> float:
+        """One pass over a (pinned) host array [N, D].  Per step, on a copy stream and double-buffered so that it overlaps
+        the previous step: the batch's rows cross the bus into a staging buffer - a plain asynchronous copy of a
+        contiguous slice, or with ``perm`` (the epoch's shuffle, includes/utils.py:450-454) a gather kernel that reads the
+        rows ``perm[lo:lo+B]`` straight from the pinned host array (dmvae_gather_rows) - then the training step, and an
+        asynchronous read of its loss.  One synchronisation at the end.  Returns the mean batch loss
+        (base_models.py:130)."""
         N = host.shape[0]
         nb = (N + batch_size - 1) // batch_size
         if max_steps is not None:
@@ -1377,6 +1417,19 @@ class Engine:
             self._loss_log = torch.zeros(nb, 4, dtype=torch.float32, device=dev)
             self._loss_host = torch.zeros(nb, 4, dtype=torch.float32).pin_memory()
         cur = torch.cuda.current_stream(dev)
+        perm_dev = None
+        if perm is not None:
+            if not host.is_pinned():
+                raise ValueError("run_epoch(perm=...) gathers from the host array on the device: it must be pinned")
+            if getattr(self, "_perm_dev", None) is None or self._perm_dev.numel() < N:
+                self._perm_dev = torch.empty(N, dtype=torch.int32, device=dev)
+                self._perm_pin = torch.empty(N, dtype=torch.int32).pin_memory()
+            cur.synchronize()                      # the previous epoch's gathers have consumed the old permutation
+            self._perm_pin[:N].copy_(torch.from_numpy(np.ascontiguousarray(perm[:N], dtype=np.int32)))
+            with torch.cuda.stream(self._copy_stream):
+                self._perm_dev[:N].copy_(self._perm_pin[:N], non_blocking=True)
+            perm_dev = self._perm_dev
+        row_bytes = host.shape[1] * host.element_size()
         klr, rs = kl_ratio, 1.0
         if mode == "vae":
             klr = 0.0
@@ -1389,7 +1442,12 @@ class Engine:
             with torch.cuda.stream(self._copy_stream):
                 if i >= 2:
                     self._copy_stream.wait_event(self._free[b])
-                self._stage[b][:rows].copy_(host[lo:lo + rows], non_blocking=True)
+                if perm_dev is None:
+                    self._stage[b][:rows].copy_(host[lo:lo + rows], non_blocking=True)
+                else:
+                    _abi.check(self.lib.dmvae_gather_rows(self.ctx, host.data_ptr(), host.stride(0) * host.element_size(),
+                                                          perm_dev.data_ptr() + 4 * lo, self._stage[b].data_ptr(), row_bytes,
+                                                          rows, row_bytes, C.c_void_p(self._copy_stream.cuda_stream)))
                 self._ready[b].record(self._copy_stream)
             cur.wait_event(self._ready[b])
             self.train_step(self._stage[b], rows, opt, None, None, klr, mode, rs)
@@ -1399,6 +1457,66 @@ class Engine:
         cur.synchronize()
         col = {"all": 3, "vae": 0, "prior": 3}[mode]
         return float(self._loss_host[:nb, col].sum()) / nb
+
+    def run_epoch_moe(self, host_x: torch.Tensor, host_y: torch.Tensor, batch_size: int, opt: AdamState, kl_ratio: float = 1.0,
+                      perm: Optional[np.ndarray] = None, max_steps: Optional[int] = None) -> np.ndarray:
+        """One pass of the MoE training step (models.py:194-221) over pinned host arrays X [N, D] / Y [N, O], batches staged
+        like run_epoch.  Returns per-step [supervised loss sum, error sum, recon, KL_c, KL_z, VAE loss] as a host array."""
+        N = host_x.shape[0]
+        O = host_y.shape[1]
+        nb = (N + batch_size - 1) // batch_size
+        if max_steps is not None:
+            nb = min(nb, max_steps)
+        dev = self.device
+        if batch_size > self.max_rows:
+            self._alloc_activations(batch_size)
+        key = ("moe", batch_size, host_x.dtype, O)
+        if getattr(self, "_epoch_key", None) != key:
+            self._epoch_key = key
+            self._copy_stream = torch.cuda.Stream(device=dev)
+            self._stage = [torch.empty(batch_size, self.D, dtype=host_x.dtype, device=dev) for _ in range(2)]
+            self._stage_y = [torch.empty(batch_size, O, dtype=torch.float32, device=dev) for _ in range(2)]
+            self._ready = [torch.cuda.Event() for _ in range(2)]
+            self._free = [torch.cuda.Event() for _ in range(2)]
+        if getattr(self, "_moe_log", None) is None or self._moe_log.shape[0] < nb:
+            self._moe_log = torch.zeros(nb, 6, dtype=torch.float32, device=dev)
+            self._moe_log_host = torch.zeros(nb, 6, dtype=torch.float32).pin_memory()
+        cur = torch.cuda.current_stream(dev)
+        perm_dev = None
+        if perm is not None:
+            if getattr(self, "_perm_dev", None) is None or self._perm_dev.numel() < N:
+                self._perm_dev = torch.empty(N, dtype=torch.int32, device=dev)
+                self._perm_pin = torch.empty(N, dtype=torch.int32).pin_memory()
+            cur.synchronize()
+            self._perm_pin[:N].copy_(torch.from_numpy(np.ascontiguousarray(perm[:N], dtype=np.int32)))
+            with torch.cuda.stream(self._copy_stream):
+                self._perm_dev[:N].copy_(self._perm_pin[:N], non_blocking=True)
+            perm_dev = self._perm_dev
+        xb, yb = host_x.shape[1] * host_x.element_size(), O * 4
+        cs = C.c_void_p(self._copy_stream.cuda_stream)
+        for i in range(nb):
+            b = i & 1
+            lo = i * batch_size
+            rows = min(batch_size, N - lo)
+            with torch.cuda.stream(self._copy_stream):
+                if i >= 2:
+                    self._copy_stream.wait_event(self._free[b])
+                if perm_dev is None:
+                    self._stage[b][:rows].copy_(host_x[lo:lo + rows], non_blocking=True)
+                    self._stage_y[b][:rows].copy_(host_y[lo:lo + rows], non_blocking=True)
+                else:
+                    ix = perm_dev.data_ptr() + 4 * lo
+                    _abi.check(self.lib.dmvae_gather_rows(self.ctx, host_x.data_ptr(), xb, ix, self._stage[b].data_ptr(), xb, rows, xb, cs))
+                    _abi.check(self.lib.dmvae_gather_rows(self.ctx, host_y.data_ptr(), yb, ix, self._stage_y[b].data_ptr(), yb, rows, yb, cs))
+                self._ready[b].record(self._copy_stream)
+            cur.wait_event(self._ready[b])
+            self.moe_step(self._stage[b], self._stage_y[b], rows, opt, kl_ratio=kl_ratio, graph=True)
+            self._moe_log[i, :2].copy_(self.moe_loss, non_blocking=True)
+            self._moe_log[i, 2:].copy_(self.loss_out, non_blocking=True)
+            self._free[b].record(cur)
+        self._moe_log_host[:nb].copy_(self._moe_log[:nb], non_blocking=True)
+        cur.synchronize()
+        return self._moe_log_host[:nb].numpy().copy()
 
     def launches(self) -> int:
         """Kernels launched so far: direct launches counted by the library + nodes of replayed CUDA graphs."""

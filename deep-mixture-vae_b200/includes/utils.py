@@ -29,10 +29,13 @@ def hungarian_accuracy(d: np.ndarray, size: int) -> float:
 
 
 def get_clustering_accuracy(weights, classes):
-    """includes/utils.py:22-34."""
+    """includes/utils.py:22-34.  The contingency matrix is sized to hold every class label too (the reference sizes it
+    by the number of clusters only and raises IndexError when there are fewer clusters than classes, e.g. the
+    `--n_experts 4` runs of runOur.sh on 10-class data); identical result whenever the reference's succeeds."""
     weights = np.asarray(weights)
     clusters = np.argmax(weights, axis=-1)
-    n_classes = weights.shape[1]
+    classes = np.asarray(classes)
+    n_classes = max(weights.shape[1], int(classes.max()) + 1 if classes.size else 0)
     size = len(clusters)
     d = np.zeros((n_classes, n_classes), dtype=np.int64)
     np.add.at(d, (clusters, np.asarray(classes).astype(np.int64)), 1)
@@ -108,7 +111,27 @@ def load_data(datagroup, output_dim=1, classification=True, **args):
         ds = _synthetic("synthetic_mnist", args.get("n_train", 55000), args.get("n_test", 10000), 784, True)
     elif datagroup == "synthetic_cifar":
         ds = _synthetic("synthetic_cifar", args.get("n_train", 50000), args.get("n_test", 10000), 3072, False)
-    elif datagroup in ("mnist", "hhar", "cifar10", "reuters", "reuters10k"):
+    elif datagroup in ("mnist", "cifar10"):
+        # the reference downloads these (utils.py:122-148, :204-210); offline, DMVAE_DATA_DIR/<name>.npz (arrays
+        # train_data, train_classes, test_data, test_classes) is used when present, else the synthetic stand-in of the
+        # same shape - so that the reference's default command line (`--dataset mnist`) runs
+        import os
+        path = os.path.join(os.environ.get("DMVAE_DATA_DIR", ""), datagroup + ".npz")
+        if os.environ.get("DMVAE_DATA_DIR") and os.path.exists(path):
+            z = np.load(path)
+            ds = _Bag()
+            ds.datagroup = datagroup
+            ds.train_data, ds.test_data = z["train_data"].astype(np.float32), z["test_data"].astype(np.float32)
+            ds.train_classes, ds.test_classes = z["train_classes"].astype(np.int64), z["test_classes"].astype(np.int64)
+            ds.n_classes, ds.input_dim, ds.input_type = 10, ds.train_data.shape[1], "binary"
+            ds.sample_plot = ds.regeneration_plot = None
+        else:
+            print("note: dataset %r is not on disk (set DMVAE_DATA_DIR); using the synthetic stand-in of the same shape" % datagroup)
+            if datagroup == "mnist":
+                ds = _synthetic("mnist", args.get("n_train", 55000), args.get("n_test", 10000), 784, True)
+            else:
+                ds = _synthetic("cifar10", args.get("n_train", 50000), args.get("n_test", 10000), 3072, False)
+    elif datagroup in ("hhar", "reuters", "reuters10k"):
         raise NotImplementedError("dataset %r needs a download (no network in this build); use 'synthetic_mnist', "
                                   "'synthetic_cifar' or 'spiral', or pass your own arrays to Dataset" % datagroup)
     else:
@@ -138,7 +161,13 @@ def _storage_dtype(data: np.ndarray):
 
 
 class Dataset:
-    """includes/utils.py:428-466.  ``data`` is (data, classes)."""
+    """includes/utils.py:428-466.  ``data`` is (data, classes).
+
+    The reference re-orders ``self.data`` in place at every epoch and builds each batch with a per-row Python append.
+    Here the rows stay where they are: an epoch is a fresh PERMUTATION (same ``np.random.permutation`` draw as the
+    reference, utils.py:450-454), ``get_batches`` yields ``data[perm[i:i+B]]`` for reference-shaped loops, and the fast
+    training path hands the permutation to the device, which gathers each batch straight out of ONE pinned host copy
+    (made once, in storage dtype) - no per-epoch host gather, no re-pinning."""
 
     def __init__(self, data, batch_size=100, shuffle=True, compact=True):
         data, classes = data
@@ -151,31 +180,36 @@ class Dataset:
         self.len = len(self.data)
         self._host: Optional[torch.Tensor] = None
         self._compact = compact
+        self.perm: Optional[np.ndarray] = None
         if shuffle:
             self._permute()
 
     def _permute(self):
-        indices = np.random.permutation(len(self.data))
-        self.data = self.data[indices]
-        self.classes = self.classes[indices]
-        self._host = None
+        self.perm = np.random.permutation(len(self.data))
 
     def host_tensor(self) -> torch.Tensor:
-        """Pinned host copy in storage dtype (uint8 for binarised data)."""
+        """Pinned host copy in storage dtype (uint8 for binarised data), rows in their ORIGINAL order; built once."""
         if self._host is None:
             dt = _storage_dtype(self.data) if self._compact else np.float32
             self._host = _pinned(self.data, dt)
         return self._host
 
     def begin_epoch(self):
-        """Reshuffle like get_batches does at the start of every epoch (utils.py:450-454)."""
+        """New epoch order, drawn like get_batches does at the start of every epoch (utils.py:450-454)."""
         if self.shuffle:
             self._permute()
+
+    def epoch_classes(self) -> np.ndarray:
+        """Classes in the order of the current epoch's batches."""
+        return self.classes if self.perm is None else self.classes[self.perm]
 
     def get_batches(self):
         self.begin_epoch()
         for i in range(0, len(self.data), self.batch_size):
-            yield self.data[i: i + self.batch_size]
+            if self.perm is None:
+                yield self.data[i: i + self.batch_size]
+            else:
+                yield self.data[self.perm[i: i + self.batch_size]]
 
     def __len__(self):
         return self.epoch_len
@@ -192,19 +226,29 @@ class MEDataset:
         self.batch_size = batch_size
         self.epoch_len = int(math.ceil(len(self.data) / batch_size))
         self.data_dim = self.data.shape[1]
+        self.perm: Optional[np.ndarray] = None
+        self._host = None
+
+    def host_tensors(self):
+        """Pinned host copies (data in storage dtype, labels float32), rows in their original order; built once."""
+        if self._host is None:
+            lab = self.labels.reshape(self.len, -1)
+            self._host = (_pinned(self.data, _storage_dtype(self.data)), _pinned(lab, np.float32))
+        return self._host
 
     def begin_epoch(self):
         if self.shuffle:
-            indices = np.random.permutation(len(self.data))
-            self.data = self.data[indices]
-            self.labels = self.labels[indices]
-            self.classes = self.classes[indices]
+            self.perm = np.random.permutation(len(self.data))
 
     def get_batches(self):
         self.begin_epoch()
         for i in range(0, len(self.data), self.batch_size):
             s = slice(i, i + self.batch_size)
-            yield self.data[s], self.labels[s], self.classes[s]
+            if self.perm is None:
+                yield self.data[s], self.labels[s], self.classes[s]
+            else:
+                ix = self.perm[s]
+                yield self.data[ix], self.labels[ix], self.classes[ix]
 
     def __len__(self):
         return self.epoch_len

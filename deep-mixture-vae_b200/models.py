@@ -9,7 +9,7 @@ from tqdm import tqdm
 
 from . import nn
 from .base_models import DeepMixtureVAE, VaDE, _to_device
-from .includes.utils import Dataset, get_clustering_accuracy
+from .includes.utils import Dataset, MEDataset, get_clustering_accuracy
 from .session import Handle
 
 
@@ -127,17 +127,22 @@ class MoE:
         return out
 
     def get_accuracy(self, session, data):
-        """models.py:121-147."""
+        """models.py:121-147.  Two notes: (1) the reference fetches ``self.vae.logits``, which its VaDE does not define
+        (VaDEMoE.get_accuracy raises AttributeError there); here a VaDE gate is scored by its cluster posterior, whose
+        argmax is what the clustering accuracy needs.  (2) the batches come in the epoch's shuffled order, so the
+        classes are collected from the batches themselves (the reference's MEDataset re-orders ``data.classes`` in place)."""
         error = 0.0
-        logits = []
-        for X_batch, Y_batch, _ in data.get_batches():
+        logits, classes = [], []
+        gate = self.vae.logits if hasattr(self.vae, "logits") else self.vae.cluster_probs
+        for X_batch, Y_batch, C_batch in data.get_batches():
             feed = {self.X: X_batch, self.Y: Y_batch}
             feed.update(self.vae.sample_reparametrization_variables(len(X_batch)))
-            batchLogits, batchError = session.run([self.vae.logits, self.error], feed_dict=feed)
+            batchLogits, batchError = session.run([gate, self.error], feed_dict=feed)
             error += batchError
             logits.append(batchLogits)
+            classes.append(C_batch)
         logits = np.concatenate(logits, axis=0)
-        accClustering = get_clustering_accuracy(logits, data.classes)
+        accClustering = get_clustering_accuracy(logits, np.concatenate(classes, axis=0))
         if self.classification:
             error /= data.len
             return 1 - error, accClustering
@@ -154,6 +159,8 @@ class MoE:
     def train_op(self, session, data, kl_ratio=1.0):
         """models.py:194-221: returns (loss, batch_acc of the last batch, lossCls)."""
         assert(self.train_step is not None)
+        if isinstance(data, MEDataset):
+            return self._train_epoch_fast(session, data, kl_ratio)
         loss = 0.0
         lossCls = 0.0
         batch_error, Y_batch = 0.0, None
@@ -168,6 +175,28 @@ class MoE:
             batch_acc = 1 - batch_error / Y_batch.shape[0]
         else:
             batch_acc = -batch_error
+        return loss, batch_acc, lossCls
+
+    def _train_epoch_fast(self, session, data, kl_ratio=1.0):
+        """models.py:194-221 with this package's MEDataset: the epoch's permutation goes to the device, which gathers each
+        batch (X and Y) out of the pinned host copies; noise comes from the device Philox generator; the step is a replayed
+        CUDA graph; one synchronisation per epoch.  Same return value: (loss, batch_acc of the last batch, lossCls)."""
+        eng = self._engine(session)
+        opt = eng.optimizer("moe", self._lr["moe"])
+        data.begin_epoch()
+        hx, hy = data.host_tensors()
+        log = eng.run_epoch_moe(hx, hy, data.batch_size, opt, kl_ratio, perm=data.perm)
+        nb = len(log)
+        last_rows = data.len - (nb - 1) * data.batch_size if nb == data.epoch_len else data.batch_size
+        rows = np.full(nb, data.batch_size, np.float64)
+        rows[-1] = last_rows
+        sup = log[:, 0] / rows                                  # batch means of the supervised loss
+        lossCls = float(np.sum(sup) / data.epoch_len)
+        loss = float(np.sum(sup + (log[:, 5] if self.lossVAE else 0.0)) / data.epoch_len)
+        if self.classification:
+            batch_acc = 1 - float(log[-1, 1]) / last_rows
+        else:
+            batch_acc = -float(log[-1, 1]) / last_rows
         return loss, batch_acc, lossCls
 
     def debug(self, session, data, kl_ratio=1.0):

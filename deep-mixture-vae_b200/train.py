@@ -62,7 +62,7 @@ def main(argv):
     model_str, model_name = argv.model, argv.model_name
     moe = model_str[-3:] == "moe"
     extra = {}
-    if argv.data_n is not None and argv.dataset.startswith("synthetic"):
+    if argv.data_n is not None and (argv.dataset.startswith("synthetic") or argv.dataset in ("mnist", "cifar10")):
         extra = dict(n_train=argv.data_n, n_test=max(1000, argv.data_n // 5))
     dataset = load_data(argv.dataset, classification=argv.classification, output_dim=argv.output_dim, **extra)
     print(dataset.input_type)

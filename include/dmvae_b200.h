@@ -105,6 +105,13 @@ int dmvae_linear_wgrad(dmvae_ctx* ctx, int dtype, const void* X, int64_t ldx, co
 int dmvae_stage_input(dmvae_ctx* ctx, const void* X, int x_dtype, int64_t ldx, void* A0, int out_dtype,
                       int64_t ld_out, int rows, int D, void* stream);
 
+/* Shuffled minibatch: dst[i, :] = src[idx[i], :], row_bytes per row (replaces the per-row Python append of
+ * Dataset.get_batches, includes/utils.py:449-463).  idx is a DEVICE int32 array; src may be a PINNED HOST buffer
+ * (unified addressing: the kernel reads it over PCIe / NVLink-C2C, so the shuffle costs no host-side gather and the
+ * rows cross the bus exactly once); dst is device memory.  Rows and pitches must be 4-byte multiples (16 for speed). */
+int dmvae_gather_rows(dmvae_ctx* ctx, const void* src, int64_t src_pitch_bytes, const int32_t* idx, void* dst,
+                      int64_t dst_pitch_bytes, int rows, int row_bytes, void* stream);
+
 /* ---- reparameterisation: priors.py:86-89 (Z), :170-181 (concrete), utils.py:17-19 (Gumbel),
  *      host RNG of priors.py:67-68 replaced by Philox4x32-10 ------------------------------------ */
 typedef struct dmvae_reparam_args {
