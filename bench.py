@@ -1,22 +1,29 @@
 #!/usr/bin/env python
-"""Benchmark of the DMVAE training step (BASELINE.json: "DMVAE train samples/sec (fwd+bwd ELBO)").
+"""Benchmark of the DMVAE / VaDE / MoE training step (BASELINE.json: "DMVAE train samples/sec (fwd+bwd ELBO) at
+1/2/4/8 B200; ELBO-kernel HBM GB/s").
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--config 2] [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
-Workload = BASELINE.json configs[1]: DMVAE, MNIST-shaped binarised 784-d synthetic data, K=10 clusters, latent 10,
-batch 4096 per GPU, bf16 tcgen05 GEMMs.  One step = encoder -> Philox reparameterisation -> decoder -> fused ELBO
-fwd+bwd -> gradient GEMMs -> (gradient reduction over NVLink for N>1) -> Adam.
+--config picks a BASELINE.json configuration (scripts/configs.py); the default, 2, is the one the metric is quoted on
+(DMVAE, MNIST-shaped binarised 784-d, K=10, latent 10, batch 4096 per GPU, bf16 tcgen05 GEMMs).  One step = encoder ->
+Philox reparameterisation -> decoder -> fused ELBO fwd+bwd -> gradient GEMMs -> (gradient exchange over NVLink for N>1)
+-> Adam.
 
-`value`      : samples/s with the batches already resident in HBM (CUDA events, max over ranks).
-`e2e`        : same metric through the public API (engine.run_epoch, the body of model.train_op) with the data in
-               pinned HOST memory: per step an H2D copy of the batch and a D2H read of the loss inside the timed region.
-`roofline`   : the fused ELBO kernel (HBM-bound): algorithmic bytes per launch / mean CUDA-event duration of that
-               launch inside the timed region, against MEASURED_PEAKS.json.
+`value`       : samples/s with the batches already resident in HBM (CUDA events around exactly K steps, max over ranks).
+`e2e`         : the same metric through the reference-facing plugin call, `model.train_op(session, Dataset)` of
+                dmvae_b200.base_models / .models, with the data in pinned HOST memory: every step the batch's rows (the
+                epoch's shuffle) cross the bus into the device inside the timed region, and the step's loss goes back.
+`roofline`    : the dominant kernel family, the tcgen05 GEMMs (tensor bound): algorithmic FLOPs per step / sum of the
+                device times of the step's GEMM launches (each launch replayed back to back in a CUDA graph with the
+                engine's own arguments and timed with CUDA events), against MEASURED_PEAKS.json's sustained bf16 rate;
+                `step_frac` is the same FLOPs over the whole timed step.
+`roofline_elbo`: the fused ELBO kernel(s) (HBM bound): algorithmic bytes / device time over rotating buffers.
 `cpu_baseline`: the CPU restatement of the reference step (oracle/, kind "port": TensorFlow 1.x is not installable)
-               timed on this box's host cores on a bounded sample.
---impl reference times that CPU restatement on the same config.
+                timed on this box's host cores on a bounded sample.
+--impl reference times that CPU restatement on the same config (rank 0 only).
 """
 import argparse
+import ctypes as C
 import json
 import os
 import subprocess
@@ -26,14 +33,11 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "scripts"))
+import configs as CFG  # noqa: E402
 
 METRIC = "DMVAE train samples/sec (fwd+bwd ELBO)"
 UNIT = "samples/s"
-D, L, K = 784, 10, 10
-BATCH_PER_GPU = 4096
-TRUNK, HEAD, DEC = (500, 500), 2000, (2000, 500, 500)
-FLOP_PER_SAMPLE = 25.40e6                      # 6*sum(Kin*Nout) - 2*D*H1
-ELBO_BYTES_PER_SAMPLE = (1 + 2 + 2) * D + 4 * (3 * L + K) + 4 * (2 * L + K) + 4 * K + 4 * L + 12   # u8 X, bf16 logits/grad: 4292
 
 
 def peaks():
@@ -91,23 +95,144 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def synth_batches(n_rows, seed=1):
-    import numpy as np
-    rng = np.random.RandomState(seed)
-    return (rng.uniform(size=(n_rows, D)) < 0.1307).astype(np.uint8)
-
-
 def dbg(msg):
     if os.environ.get("DMVAE_BENCH_DEBUG"):
         print("[bench %s] %s" % (os.environ.get("RANK", "0"), msg), file=sys.stderr, flush=True)
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# model construction through the reference-facing API
+# ---------------------------------------------------------------------------------------------------------------
+def build_model(cfg, B, gemm_dtype):
+    from dmvae_b200 import base_models, models, nn
+    kw = dict(activation=nn.relu, initializer=nn.xavier_initializer)
+    if cfg["model"] == "dmvae":
+        m = base_models.DeepMixtureVAE("dmvae", "binary", cfg["D"], cfg["L"], cfg["K"], hidden=cfg["trunk"] + (cfg["head"],),
+                                       decoder=cfg["decoder"], **kw).build_graph()
+        vae = m
+    elif cfg["model"] == "vade":
+        m = base_models.VaDE("vade", "binary", cfg["D"], cfg["L"], cfg["K"], hidden=cfg["trunk"], decoder=cfg["decoder"],
+                             **kw).build_graph()
+        vae = m
+    else:                                           # runLR_MOE.sh: dmoe --classification --n_experts E
+        m = models.DeepMoE("dmoe", "binary", cfg["D"], cfg["output_dim"], cfg["n_experts"], True, **kw).build_graph()
+        vae = m.vae
+    m.gemm_dtype = gemm_dtype
+    vae.gemm_dtype = gemm_dtype
+    vae.max_batch = B
+    vae.seed = 0
+    m.define_train_step(0.002, 100)
+    return m, vae
+
+
+def make_dataset(cfg, n_rows, B, seed):
+    """Synthetic inputs wrapped in this package's Dataset / MEDataset (pinned host copy made once)."""
+    import numpy as np
+    from dmvae_b200.includes.utils import Dataset, MEDataset
+    X = CFG.synth_inputs(cfg, n_rows, seed)
+    cls = (np.arange(n_rows) % 10).astype(np.int64)
+    if cfg["model"] == "dmoe":
+        Y = np.eye(cfg["output_dim"], dtype=np.float32)[cls % cfg["output_dim"]]
+        return MEDataset((X, cls, Y), batch_size=B)
+    return Dataset((X.astype(np.float32) if not cfg["binarised"] else X, cls), batch_size=B)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# per-launch device times: every GEMM launch of one step, with the engine's own arguments
+# ---------------------------------------------------------------------------------------------------------------
+class _Recorder:
+    """Proxy of the ctypes library that records the GEMM entry points an eager step calls (and still executes them)."""
+    GEMM = ("dmvae_gemm", "dmvae_linear_fwd", "dmvae_linear_dgrad", "dmvae_linear_wgrad", "dmvae_gemm_chain")
+
+    def __init__(self, lib):
+        self._lib, self.calls, self.on = lib, [], False
+
+    def __getattr__(self, name):
+        fn = getattr(self._lib, name)
+        if name not in self.GEMM:
+            return fn
+
+        def wrapped(*args):
+            if self.on:
+                self.calls.append((name, fn, args))
+            return fn(*args)
+        return wrapped
+
+
+def graph_time_us(torch, dev, fn, n_inst=20):
+    fn()
+    torch.cuda.synchronize(dev)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(n_inst):
+            fn()
+    g.replay()
+    torch.cuda.synchronize(dev)
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    g.replay()
+    t1.record()
+    torch.cuda.synchronize(dev)
+    del g
+    return t0.elapsed_time(t1) * 1e3 / n_inst
+
+
+def time_gemm_launches(torch, eng, run_eager_step, dev):
+    """Sum of the device times (us) of the step's GEMM launches + their count."""
+    from dmvae_b200 import _abi
+    rec = _Recorder(eng.lib)
+    eng.lib = rec
+    try:
+        torch.cuda.synchronize(dev)
+        rec.on = True
+        run_eager_step()
+        rec.on = False
+        torch.cuda.synchronize(dev)
+    finally:
+        eng.lib = rec._lib
+    total, rows = 0.0, []
+    st = lambda: C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    for name, fn, args in rec.calls:
+        a = list(args)
+        call = lambda: _abi.check(fn(*(a[:-1] + [st()])))       # same arguments, current (capturing) stream
+        us = graph_time_us(torch, dev, call)
+        total += us
+        rows.append((name, us))
+    return total, rows
+
+
+def time_elbo(torch, eng, X, xdt, B, world, dev, n_inst=20):
+    """Device time (us) of one fused-ELBO call (all its kernels) over rotating copies of the D-wide buffers, so that the
+    working set exceeds L2 whenever the size allows."""
+    from dmvae_b200 import _abi
+    per = X[:B].numel() * X.element_size() + 2 * eng.decoded[:B].numel() * eng.decoded.element_size()
+    nrot = max(2, min(16, int(300e6 // per) + 1))
+    sets = []
+    for i in range(nrot):
+        sets.append((X[:B].clone(), eng.decoded[:B].clone(), torch.empty_like(eng.ddecoded[:B])))
+    eas = []
+    for Xi, di, gi in sets:
+        ea = eng._elbo_args(Xi, xdt, B, 1.0, 1.0 / (world * B))
+        ea.decoded, ea.d_decoded = di.data_ptr(), gi.data_ptr()
+        eas.append(ea)
+    it = [0]
+
+    def call():
+        ea = eas[it[0] % nrot]
+        it[0] += 1
+        _abi.check(eng.lib.dmvae_elbo_fwd_bwd(eng.ctx, C.byref(ea), eng._stream()))
+    return graph_time_us(torch, dev, call, n_inst), nrot, per * nrot
+
+
+# ---------------------------------------------------------------------------------------------------------------
 def run_ours(args):
     import numpy as np
     import torch
     import torch.distributed as dist
-    from dmvae_b200.engine import Engine
+    from dmvae_b200 import _abi
+    from dmvae_b200.session import Session
 
+    cfg = CFG.CONFIGS[args.config]
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -116,27 +241,37 @@ def run_ours(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    B = BATCH_PER_GPU
-    eng = Engine(model="dmvae", input_type="binary", input_dim=D, latent_dim=L, n_classes=K, trunk=TRUNK, head=HEAD,
-                 decoder=DEC, name="dmvae", gemm_dtype="bf16", max_rows=B, device=dev, seed=0)
+    strong = cfg["scaling"] == "strong"
+    B = cfg["batch"] // world if strong else cfg["batch"]           # rows per GPU
+    K_, W_ = args.steps, args.warmup
+    is_moe = cfg["model"] == "dmoe"
+
+    model, vae = build_model(cfg, B, args.gemm_dtype)
+    sess = Session(device=local_rank)
+    eng = vae._ensure_engine(sess)
     dp = None
     if world > 1:
+        if is_moe:
+            raise SystemExit("config 4 (LR-MoE) is a single-GPU configuration")
         from dmvae_b200.dp import DataParallel
         dp = DataParallel(eng, mode=args.dp_mode)
-    opt = eng.optimizer("train", 0.002)
-    NB = 16                                                         # resident batches rotated through (51 MB of u8)
-    host = torch.from_numpy(synth_batches(NB * B, seed=1 + rank)).pin_memory()
-    resident = host.to(dev)
-    K_, W_ = args.steps, args.warmup
-
-    xs = torch.empty(B, D, dtype=torch.uint8, device=dev)           # static input buffer of the captured step
+    opt = eng.optimizer("moe" if is_moe else "train", 0.002)
+    xdtype = torch.uint8 if cfg["binarised"] else torch.float32
+    xdt = _abi.U8 if cfg["binarised"] else _abi.F32
+    row_bytes = cfg["D"] * (1 if cfg["binarised"] else 4)
+    NB = max(2, min(16, int(260e6 // (B * row_bytes))))             # resident batches rotated through
+    resident = torch.from_numpy(CFG.synth_inputs(cfg, NB * B, seed=1 + rank)).to(dev)
+    xs = torch.empty(B, cfg["D"], dtype=xdtype, device=dev)          # static input buffer of the captured step
+    ys = None
+    if is_moe:
+        ys = torch.nn.functional.one_hot(torch.arange(B) % cfg["output_dim"], cfg["output_dim"]).float().to(dev)
 
     def step(i):
-        xs.copy_(resident[(i % NB) * B:(i % NB + 1) * B], non_blocking=True)     # device-to-device, 3.2 MB
-        if dp is None:
-            eng.train_step(xs, B, opt)
+        xs.copy_(resident[(i % NB) * B:(i % NB + 1) * B], non_blocking=True)     # device-to-device
+        if is_moe:
+            eng.moe_step(xs, ys, B, opt, graph=True)
         else:
-            dp.train_step(xs, B, opt)
+            eng.train_step(xs, B, opt)
 
     def barrier():
         if world > 1:
@@ -147,7 +282,6 @@ def run_ours(args):
     for i in range(W_):
         step(i)
     barrier()
-    dbg("warmup done")
     # ---- timed region 1: inputs resident in HBM ----
     clocks = ClockSampler(local_rank)
     if rank == 0:
@@ -161,67 +295,37 @@ def run_ours(args):
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
-    dbg("region 1 done: %.3f ms/step" % (ms / K_))
     launches = eng.launches() - l0
-    # ---- timed region 2: end to end from pinned host memory through the public epoch loop ----
-    NBH = min(K_, 128)                                              # host-resident batches of the e2e pass (<= 411 MB pinned)
-    if NBH > NB:
-        host = torch.from_numpy(synth_batches(NBH * B, seed=1 + rank)).pin_memory()
-    eng.run_epoch(host, B, opt, max_steps=min(W_, NBH)) if dp is None else dp.run_epoch(host, B, opt, max_steps=min(W_, NBH))
+    dbg("region 1 done: %.3f ms/step" % (ms / K_))
+    # ---- timed region 2: end to end through model.train_op(session, Dataset) from pinned host memory ----
+    nb_host = max(d for d in range(1, 65) if K_ % d == 0)            # batches per epoch: a divisor of K (<= 64 batches pinned)
+    while nb_host * B * row_bytes > 700e6 and nb_host > 1:
+        nb_host = max(d for d in range(1, nb_host) if K_ % d == 0)
+    data = make_dataset(cfg, nb_host * B, B, seed=1 + rank)
+    for _ in range(max(1, (W_ + nb_host - 1) // nb_host)):
+        model.train_op(sess, data, 1.0)
     barrier()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
-    done = 0
-    while done < K_:
-        n = min(NBH, K_ - done)
-        (eng.run_epoch(host, B, opt, max_steps=n) if dp is None else dp.run_epoch(host, B, opt, max_steps=n))
-        done += n
+    for _ in range(K_ // nb_host):
+        model.train_op(sess, data, 1.0)
     e3.record()
     barrier()
     ms_e2e = e2.elapsed_time(e3)
     dbg("region 2 done: %.3f ms/step" % (ms_e2e / K_))
     clk = clocks.stop() if rank == 0 else None
-    # ---- timed region 3: per-kernel device times.  Each kernel is launched `n_inst` times back to back inside one
-    #      CUDA graph on this rank's own step buffers and the replay is bracketed by CUDA events on the launching
-    #      stream (an event pair around a single eager launch would mostly measure the host's launch gap).  The
-    #      ELBO operands are L2-warm, as they are in the step (the decoder GEMM has just written them). ----
-    import ctypes as C
-    from dmvae_b200 import _abi
-    sys.path.insert(0, os.path.join(ROOT, "scripts"))
-    from gemm_bench import time_gemms
-    n_inst = 20
-
-    def graph_time_us(fn):
-        fn()
-        torch.cuda.synchronize(dev)
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            for _ in range(n_inst):
-                fn()
-        g.replay()
-        torch.cuda.synchronize(dev)
-        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t0.record()
-        g.replay()
-        t1.record()
-        torch.cuda.synchronize(dev)
-        return t0.elapsed_time(t1) * 1e3 / n_inst
-
-    ea = eng._elbo_args(xs, _abi.U8, B, 1.0, 1.0 / (world * B))
-    elbo_us = graph_time_us(lambda: _abi.check(eng.lib.dmvae_elbo_fwd_bwd(eng.ctx, C.byref(ea), eng._stream())))
+    # ---- region 3 (rank-local, not part of `value`): per-launch device times ----
+    eager = (lambda: eng.moe_step(xs, ys, B, None)) if is_moe else (lambda: eng.forward_backward(xs, B))
+    gemm_us, gemm_rows = time_gemm_launches(torch, eng, eager, dev)
+    elbo_us = elbo_nrot = elbo_ws = None
+    if not is_moe:
+        elbo_us, elbo_nrot, elbo_ws = time_elbo(torch, eng, xs, xdt, B, world, dev)
     adam_us = None
     if dp is None:
-        adam_us = graph_time_us(lambda: _abi.check(eng.lib.dmvae_adam(
+        adam_us = graph_time_us(torch, dev, lambda: _abi.check(eng.lib.dmvae_adam(
             eng.ctx, eng.params.data_ptr(), eng.grads.data_ptr(), opt.m.data_ptr(), opt.v.data_ptr(),
-            eng.params_op.data_ptr(), eng.n_params, 1e-9, None, opt.beta1, opt.beta2, opt.eps, 1.0, 1, eng._stream())))
-    # the same kernel at 16 batches' worth of rows (65 536): the launch + single-wave cost that dominates at 4096 rows
-    # amortises, which is the figure to read against the HBM roofline
-    elbo_big_rows, elbo_big_us = 16 * B, None
-    if world == 1:
-        from elbo_bench import time_elbo
-        elbo_big_us, _ = time_elbo(eng.lib, eng.ctx, elbo_big_rows, D, L, K, n_inst)
-    gemm_us_step, _, _ = time_gemms(eng.lib, eng.ctx, B, n_inst, verbose=False, dev=dev)
-    gemm_ms_step = gemm_us_step * 1e-3
+            eng.params_op.data_ptr() if eng.params_op is not None else None, eng.n_params, 1e-9, None, opt.beta1, opt.beta2,
+            opt.eps, 1.0, 1, eng._stream())))
     dbg("region 3 done")
 
     t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
@@ -234,55 +338,57 @@ def run_ours(args):
     pk = peaks()
     value = world * B * K_ / (ms * 1e-3)
     e2e = world * B * K_ / (ms_e2e * 1e-3)
-    elbo_avg_ms = elbo_us * 1e-3
-    elbo_bytes = ELBO_BYTES_PER_SAMPLE * B
-    achieved = elbo_bytes / (elbo_avg_ms * 1e-3) / 1e9
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "elbo_traffic.json")
-    if os.path.exists(tp):
-        with open(tp) as f:
-            traffic = json.load(f).get("dram_bytes_per_launch")
+    flop = CFG.gemm_flop_per_sample(cfg) * B
+    tf_launch = flop / (gemm_us * 1e-6) / 1e12
+    tf_step = flop / (ms / K_ * 1e-3) / 1e12
+    logit_bytes = 2 if args.gemm_dtype == "bf16" else 4
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K_, "warmup": W_,
-        "ms_per_step": ms / K_, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
-        "data": "synthetic",
-        "config": {"workload": "DMVAE MNIST-shaped binarised 784-d, K=10, latent 10, batch 4096 per GPU, bf16 GEMMs "
-                               "(BASELINE.json configs[1])",
-                   "batch_per_gpu": B, "global_batch": world * B, "hidden": "784-500-500-2000 / 2000-500-500-784",
+        "ms_per_step": ms / K_, "higher_is_better": True, "scaling": cfg["scaling"], "vs_baseline": None,
+        "dtype": "bf16" if args.gemm_dtype == "bf16" else "f32", "data": "synthetic",
+        "config": {"workload": cfg["workload"], "config_id": args.config, "batch_per_gpu": B, "global_batch": world * B,
                    "parallelism": "dp%d" % world if world > 1 else "single",
                    "exchange": None if dp is None else (dp.mode + ("+nvls" if getattr(dp, "_mc", 0) else "")),
-                   "l2": "per-step working set ~240 MB (> 126 MB L2); inputs rotate over 16 resident batches",
+                   "l2": "inputs rotate over %d resident batches; per-step working set (activations + gradients + Adam) "
+                         "exceeds the 126 MB L2" % NB,
                    "noise": "device Philox4x32-10", "optimizer": "Adam (TF semantics), every step"},
-        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": world * B * D, "d2h_bytes_per_step": world * 16,
-                "ms_per_step": ms_e2e / K_, "api": "Engine.run_epoch (body of model.train_op) from pinned host uint8"},
+        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": world * B * row_bytes + (world * B * cfg.get("output_dim", 0) * 4 if is_moe else 0),
+                "d2h_bytes_per_step": world * (24 if is_moe else 16), "ms_per_step": ms_e2e / K_,
+                "api": "model.train_op(Session(), %s(...)): %d epochs of %d batches; rows gathered by permutation index from the "
+                       "pinned host array by a copy-stream kernel (zero-copy reads), loss read back per step"
+                       % ("MEDataset" if is_moe else "Dataset", K_ // nb_host, nb_host)},
         "gpu_launches": int(launches),
         "clocks": clk,
-        "roofline": {"kernel": "elbo_rowtile_kernel<u8,bf16,binary> (fused ELBO fwd+bwd)", "bound": "hbm", "achieved": achieved,
-                     "peak": pk["hbm"], "unit": "GB/s", "frac": achieved / pk["hbm"], "traffic": traffic,
-                     "peak_source": pk["src"], "bytes_per_launch": elbo_bytes, "us_per_launch": elbo_avg_ms * 1e3,
-                     "timing": "CUDA events around a graph replay of 20 launches on the step's own buffers (L2-warm, as in the step)",
-                     "large_batch": None if elbo_big_us is None else {
-                         "rows": elbo_big_rows, "us_per_launch": elbo_big_us,
-                         "achieved": ELBO_BYTES_PER_SAMPLE * elbo_big_rows / elbo_big_us * 1e-3,
-                         "frac": ELBO_BYTES_PER_SAMPLE * elbo_big_rows / elbo_big_us * 1e-3 / pk["hbm"],
-                         "note": "same kernel, 65 536 rows, inputs rotating over > L2"}},
-        "roofline_gemm": {"bound": "tensor", "achieved": FLOP_PER_SAMPLE * B / (gemm_ms_step * 1e-3) / 1e12,
-                          "peak": pk["tf_sust"], "unit": "TFLOP/s",
-                          "frac": FLOP_PER_SAMPLE * B / (gemm_ms_step * 1e-3) / 1e12 / pk["tf_sust"],
-                          "gemm_ms_per_step": gemm_ms_step,
-                          "note": "algorithmic FLOPs (25.40 MFLOP/sample) / sum of the device times of the step's 27 GEMM "
-                                  "launches, each timed as a CUDA-graph replay of 20 back-to-back launches"},
+        "roofline": {"kernel": "tcgen05 GEMM family: gemm_tc2_kernel / gemm_chain_kernel / gemm_tc_kernel (%d launches per step)" % len(gemm_rows),
+                     "bound": "tensor", "achieved": tf_launch, "peak": pk["tf_sust"], "unit": "TFLOP/s",
+                     "frac": tf_launch / pk["tf_sust"], "traffic": None, "peak_source": pk["src"],
+                     "flop_per_step": flop, "us_per_step": gemm_us, "step_frac": tf_step / pk["tf_sust"],
+                     "timing": "every GEMM launch of one step re-issued with the engine's own arguments, 20x back to back in a "
+                               "CUDA graph, CUDA events on the launching stream; step_frac = the same FLOPs over the whole timed step"},
         "adam_us": adam_us,
     }
+    if elbo_us is not None:
+        eb = CFG.elbo_bytes_per_sample(cfg, 1 if cfg["binarised"] else 4, logit_bytes) * B
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "r02_elbo_traffic.json")
+        if os.path.exists(tp):
+            with open(tp) as f:
+                traffic = json.load(f).get("cfg%d" % args.config)
+        out["roofline_elbo"] = {"kernel": "fused ELBO fwd+bwd (elbo_rowtile_kernel, or elbo_latent_mma_kernel + elbo_recon_kernel)",
+                                "bound": "hbm", "achieved": eb / (elbo_us * 1e-6) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
+                                "frac": eb / (elbo_us * 1e-6) / 1e9 / pk["hbm"], "traffic": traffic, "bytes_per_launch": eb,
+                                "us_per_launch": elbo_us,
+                                "timing": "CUDA events around a graph replay of 20 calls over %d rotating buffer sets (%.0f MB)"
+                                          % (elbo_nrot, elbo_ws / 1e6)}
     if world == 1 and not args.no_cpu_baseline:
-        out["cpu_baseline"] = cpu_baseline(bounded_seconds=20.0)
+        out["cpu_baseline"] = cpu_baseline(cfg, bounded_seconds=20.0)
     print(json.dumps(out), flush=True)
     _finish(world, dev)
 
 
 def _finish(world, dev):
-    """Multi-rank teardown: captured graphs hold NCCL / symmetric-memory work, and destroying the process group under
-    them can block; every rank synchronises and leaves without running the destructors."""
+    """Multi-rank teardown: captured graphs hold symmetric-memory work, and destroying the process group under them can
+    block; every rank synchronises and leaves without running the destructors."""
     if world > 1:
         import torch
         torch.cuda.synchronize(dev)
@@ -291,16 +397,27 @@ def _finish(world, dev):
         os._exit(0)
 
 
-def cpu_baseline(bounded_seconds=20.0, batch=256):
-    """CPU restatement of the reference step (oracle/cpu_train.py) at the reference's CPU-runnable config
-    (configs[0]: batch 256) on a bounded sample."""
-    from oracle import cpu_train
+def _oracle_cfg(cfg):
     from oracle import reference_graph as rg
+    if cfg["model"] == "vade":
+        return rg.GraphConfig.vade(input_dim=cfg["D"], latent_dim=cfg["L"], n_classes=cfg["K"], trunk=cfg["trunk"],
+                                   decoder=cfg["decoder"]), None
+    g = rg.GraphConfig(input_dim=cfg["D"], latent_dim=cfg["L"], n_classes=cfg["K"], trunk=cfg["trunk"], head=cfg["head"],
+                       decoder=cfg["decoder"])
+    moe = dict(n_experts=cfg["n_experts"], output_dim=cfg["output_dim"]) if cfg["model"] == "dmoe" else None
+    return g, moe
+
+
+def cpu_baseline(cfg, bounded_seconds=20.0):
+    """CPU restatement of the reference step (oracle/cpu_train.py) on a bounded sample of the same workload: the
+    reference's own CPU-runnable batch (256, BASELINE configs[0]) for the MNIST-shaped configs, 64 for the CIFAR-shaped."""
+    from oracle import cpu_train
     cores = os.cpu_count() or 1
-    cfg = rg.GraphConfig(input_dim=D, latent_dim=L, n_classes=K)
-    probe = cpu_train.time_training(cfg, batch, 3, 2, cores)
-    n = int(max(5, min(200, bounded_seconds / (probe["ms_per_step"] * 1e-3))))
-    r = cpu_train.time_training(cfg, batch, n, 3, cores)
+    g, moe = _oracle_cfg(cfg)
+    batch = 256 if cfg["D"] <= 1024 else 64
+    probe = cpu_train.time_training(g, batch, 2, 1, cores, binarised=cfg["binarised"], moe=moe)
+    n = int(max(3, min(200, bounded_seconds / (probe["ms_per_step"] * 1e-3))))
+    r = cpu_train.time_training(g, batch, n, 2, cores, binarised=cfg["binarised"], moe=moe)
     return {"value": r["samples_per_s"], "unit": UNIT, "cores": cores, "kind": "port",
             "sample": "%d steps of batch %d (median step %.1f ms, p10 %.1f, p90 %.1f), op-for-op fp32 PyTorch-CPU "
                       "restatement of the reference graph incl. Python batching and host noise" %
@@ -308,29 +425,27 @@ def cpu_baseline(bounded_seconds=20.0, batch=256):
 
 
 def run_reference(args):
-    """Reference arm: the reference's own CPU implementation of the path cannot run (TensorFlow 1.x is not
-    installable here), so this times the op-for-op CPU port in oracle/ on the same config (batch 4096 per step),
-    rank 0 only."""
+    """Reference arm: the reference's own CPU implementation of the path cannot run (TensorFlow 1.x is not installable
+    here), so this times the op-for-op CPU port in oracle/ on the same config, rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import torch
     from oracle import cpu_train
-    from oracle import reference_graph as rg
+    cfg = CFG.CONFIGS[args.config]
     cores = os.cpu_count() or 1
-    cfg = rg.GraphConfig(input_dim=D, latent_dim=L, n_classes=K)
-    batch = BATCH_PER_GPU
-    probe = cpu_train.time_training(cfg, batch, 1, 1, cores)
-    if probe["ms_per_step"] * (args.steps + args.warmup) > 240e3:      # keep the arm within a few minutes
-        batch = 1024
-    r = cpu_train.time_training(cfg, batch, args.steps, args.warmup, cores)
+    g, moe = _oracle_cfg(cfg)
+    batch = cfg["batch"]
+    probe = cpu_train.time_training(g, batch, 1, 1, cores, binarised=cfg["binarised"], moe=moe)
+    while probe["ms_per_step"] * (args.steps + args.warmup) > 240e3 and batch > 256:       # keep the arm within a few minutes
+        batch //= 4
+        probe = cpu_train.time_training(g, batch, 1, 1, cores, binarised=cfg["binarised"], moe=moe)
+    r = cpu_train.time_training(g, batch, args.steps, args.warmup, cores, binarised=cfg["binarised"], moe=moe)
     val = r["mean_samples_per_s"]
     sample = "%d steps x %d samples on %d host threads (PyTorch-CPU fp32 port of the TF graph)" % (r["steps"], batch, cores)
     out = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-           "warmup": args.warmup, "ms_per_step": 1e3 * batch / val, "higher_is_better": True, "scaling": "weak",
+           "warmup": args.warmup, "ms_per_step": 1e3 * batch / val, "higher_is_better": True, "scaling": cfg["scaling"],
            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": "DMVAE MNIST-shaped binarised 784-d, K=10, latent 10, batch 4096 per GPU "
-                                  "(BASELINE.json configs[1]) - CPU port", "sample_batch": batch},
+           "config": {"workload": cfg["workload"], "config_id": args.config, "sample_batch": batch},
            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
@@ -340,9 +455,11 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--config", type=int, default=2, choices=sorted(CFG.CONFIGS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--gemm_dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--dp_mode", default="auto")
     ap.add_argument("--no_cpu_baseline", action="store_true")
     args = ap.parse_args()

@@ -22,6 +22,24 @@ bool dmvae_pdl_enabled() {
   return v == 1;
 }
 
+void dmvae_prepare_kernel(const void* kern) {
+  static thread_local const void* last = nullptr;
+  if (kern == last) return;
+  last = kern;
+  static std::mutex mu;
+  static std::unordered_map<const void*, int> seen;
+  static int enabled = -1;
+  std::lock_guard<std::mutex> g(mu);
+  if (enabled < 0) {
+    const char* e = getenv("DMVAE_CARVEOUT");
+    enabled = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (!enabled || seen.count(kern)) return;
+  seen[kern] = 1;
+  (void)cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+  (void)cudaGetLastError();
+}
+
 extern "C" int dmvae_abi_version(void) { return DMVAE_B200_ABI_VERSION; }
 extern "C" const char* dmvae_last_error(void) { return g_err; }
 
@@ -222,27 +240,32 @@ extern "C" int dmvae_stage_input(dmvae_ctx* ctx, const void* X, int x_dtype, int
 // ---------------------------------------------------------------------------------------------
 // shuffled minibatch gather (source may be pinned host memory: zero-copy reads)
 // ---------------------------------------------------------------------------------------------
+// Background launch shape (see adam_bg_kernel): 4-warp blocks of <= 48 registers, one warp per scheduler, so that a block
+// fits BESIDE a resident tcgen05 GEMM CTA.  The reads are bus-latency bound when the source is host memory, so a block
+// lives for tens of microseconds: a 256-thread block would not fit next to a GEMM CTA and the step's persistent GEMM
+// launches would wait for the gather's blocks to drain (measured: e2e 0.43 instead of 0.31 ms per step).
 template <typename V>
-__global__ void __launch_bounds__(256) gather_rows_kernel(const uint8_t* __restrict__ src, int64_t src_pitch,
-                                                           const int32_t* __restrict__ idx, uint8_t* __restrict__ dst,
-                                                           int64_t dst_pitch, int rows, int vecs_per_row) {
+__global__ void __launch_bounds__(128, 12) gather_rows_kernel(const uint8_t* __restrict__ src, int64_t src_pitch,
+                                                              const int32_t* __restrict__ idx, uint8_t* __restrict__ dst,
+                                                              int64_t dst_pitch, int rows, int vecs_per_row) {
   // flat over (row, vector): consecutive threads read consecutive 16-byte (4-byte) pieces of a row; four independent
-  // loads in flight per thread - the reads are bus-latency bound when the source is host memory
+  // loads in flight per thread (<= 40 registers)
+  constexpr int U = 4;
   const int64_t total = (int64_t)rows * vecs_per_row;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  for (; i + 3 * stride < total; i += 4 * stride) {
-    V v[4];
-    int64_t r[4], c[4];
+  for (; i + (U - 1) * stride < total; i += U * stride) {
+    V v[U];
+    int r[U], c[U];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < U; ++j) {
       const int64_t e = i + j * stride;
-      r[j] = e / vecs_per_row;
-      c[j] = e - r[j] * vecs_per_row;
+      r[j] = (int)(e / vecs_per_row);
+      c[j] = (int)(e - (int64_t)r[j] * vecs_per_row);
       v[j] = *reinterpret_cast<const V*>(src + (int64_t)idx[r[j]] * src_pitch + c[j] * (int64_t)sizeof(V));
     }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) *reinterpret_cast<V*>(dst + r[j] * dst_pitch + c[j] * (int64_t)sizeof(V)) = v[j];
+    for (int j = 0; j < U; ++j) *reinterpret_cast<V*>(dst + r[j] * dst_pitch + c[j] * (int64_t)sizeof(V)) = v[j];
   }
   for (; i < total; i += stride) {
     const int64_t r = i / vecs_per_row, c = i - r * vecs_per_row;
@@ -263,13 +286,23 @@ extern "C" int dmvae_gather_rows(dmvae_ctx* ctx, const void* src, int64_t src_pi
                    ((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 15) == 0;
   const int vpr = row_bytes / (v16 ? 16 : 4);
   const int64_t total = (int64_t)rows * vpr;
-  const int blocks = (int)min((int64_t)ctx->sm_count * 8, (total + 1023) / 1024);
+  // ONE block per SM: with more, the blocks' registers crowd out the GEMM CTA of the training step running beside them
+  const int blocks = (int)min((int64_t)ctx->sm_count, (total + 511) / 512);
   cudaStream_t st = (cudaStream_t)stream;
+  // An SM whose shared-memory carveout was configured for this kernel (0 bytes: maximum L1) must drain before a
+  // tcgen05 GEMM CTA (~200 KB of shared memory) can be placed on it - the step's GEMM launches then wait for the whole
+  // gather (measured: +75 us per step).  Ask for the maximum shared-memory carveout so both kinds of block co-reside.
+  static bool carveout_set = false;
+  if (!carveout_set) {
+    DMVAE_CUDA(cudaFuncSetAttribute(gather_rows_kernel<uint4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    DMVAE_CUDA(cudaFuncSetAttribute(gather_rows_kernel<uint32_t>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    carveout_set = true;
+  }
   if (v16)
-    gather_rows_kernel<uint4><<<max(1, blocks), 256, 0, st>>>((const uint8_t*)src, src_pitch_bytes, idx, (uint8_t*)dst,
+    gather_rows_kernel<uint4><<<max(1, blocks), 128, 0, st>>>((const uint8_t*)src, src_pitch_bytes, idx, (uint8_t*)dst,
                                                               dst_pitch_bytes, rows, vpr);
   else
-    gather_rows_kernel<uint32_t><<<max(1, blocks), 256, 0, st>>>((const uint8_t*)src, src_pitch_bytes, idx, (uint8_t*)dst,
+    gather_rows_kernel<uint32_t><<<max(1, blocks), 128, 0, st>>>((const uint8_t*)src, src_pitch_bytes, idx, (uint8_t*)dst,
                                                                  dst_pitch_bytes, rows, vpr);
   DMVAE_LAUNCH_CHECK(ctx);
   return DMVAE_OK;

@@ -88,6 +88,12 @@ void dmvae_set_error(const char* fmt, ...);
 // predecessor may touch; pdl_wait() returns once the predecessor grid has completed and its writes are visible.
 // DMVAE_PDL=0 in the environment turns the attribute off (A/B measurements).
 bool dmvae_pdl_enabled();
+// First launch of a kernel through dmvae_launch: ask for the MAXIMUM shared-memory carveout.  An SM configured for a
+// kernel without shared memory (maximum L1) has to drain before a tcgen05 GEMM CTA (~200 KB of shared memory) can be
+// placed on it, and the other way round; the step interleaves small streaming kernels with GEMM launches (and runs some
+// beside them on a second stream), so every kernel of the library asks for the same carveout and the SMs never
+// reconfigure.  DMVAE_CARVEOUT=0 leaves the driver's default (A/B measurements).
+void dmvae_prepare_kernel(const void* kern);
 
 template <typename... KArgs, typename... Args>
 static inline cudaError_t dmvae_launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl,
@@ -103,6 +109,7 @@ static inline cudaError_t dmvae_launch(void (*kern)(KArgs...), dim3 grid, dim3 b
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = (pdl && dmvae_pdl_enabled()) ? 1 : 0;
+  dmvae_prepare_kernel(reinterpret_cast<const void*>(kern));
   return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 

@@ -93,6 +93,53 @@ class CpuTrainer:
         return float(loss)
 
 
+class MoeCpuTrainer:
+    """`dmoe` training step on the host (models.py:53-111, :149-163, :194-221 with DeepMoE's lossVAE=0, featLearn=0):
+    only the sub-graph that `session.run([error, loss, train_step, recon_loss])` evaluates - trunk, c-head, softmax gate,
+    tiled-input expert matmul, gated mixture, NLL x 1000 - differentiated by autograd, one TF-semantics Adam per variable."""
+
+    def __init__(self, cfg: rg.GraphConfig, variables: Dict[str, np.ndarray], n_experts, output_dim, lr=0.002, seed=2,
+                 dtype=torch.float32):
+        self.cfg, self.dtype, self.E, self.O = cfg, dtype, n_experts, output_dim
+        rs = np.random.RandomState(seed)
+        e = cfg.name + "/encoder_network"
+        keep = [e + "/dense/kernel", e + "/dense/bias", e + "/dense_1/kernel", e + "/dense_1/bias", e + "/c/dense/kernel",
+                e + "/c/dense/bias", e + "/c/dense_1/kernel", e + "/c/dense_1/bias"]
+        self.V = {k: torch.tensor(variables[k], dtype=dtype).requires_grad_(True) for k in keep}
+        self.V["W"] = torch.tensor(rs.randn(n_experts, output_dim, cfg.input_dim), dtype=dtype).requires_grad_(True)   # models.py:53-72
+        self.V["b"] = torch.zeros(output_dim, n_experts, dtype=dtype).requires_grad_(True)
+        self.names = list(self.V.keys())
+        self.m = {k: torch.zeros_like(v) for k, v in self.V.items()}
+        self.v = {k: torch.zeros_like(v) for k, v in self.V.items()}
+        self.t, self.lr = 0, lr
+        self.rng = rs
+
+    def step(self, batch, labels) -> float:
+        cfg, V = self.cfg, self.V
+        e = cfg.name + "/encoder_network"
+        B = len(batch)
+        self.rng.randn(B, cfg.latent_dim)                                # noise is drawn and fed every step (models.py:200-207)
+        rg.sample_gumbel(self.rng, (B, 1, cfg.n_classes))
+        X = torch.tensor(batch, dtype=self.dtype)
+        Y = torch.tensor(labels, dtype=self.dtype)
+        h = torch.relu(X @ V[e + "/dense/kernel"] + V[e + "/dense/bias"])
+        h = torch.relu(h @ V[e + "/dense_1/kernel"] + V[e + "/dense_1/bias"])
+        hc = torch.relu(h @ V[e + "/c/dense/kernel"] + V[e + "/c/dense/bias"])
+        gate = torch.softmax(hc @ V[e + "/c/dense_1/kernel"] + V[e + "/c/dense_1/bias"], dim=-1)
+        mo = rg.moe_forward(X, gate, V["W"], V["b"], Y, True)
+        loss = mo["recon_loss"]
+        grads = torch.autograd.grad(loss, [V[k] for k in self.names])
+        self.t += 1
+        b1, b2, eps_a = 0.9, 0.999, 1e-8
+        lr_t = self.lr * math.sqrt(1.0 - b2 ** self.t) / (1.0 - b1 ** self.t)
+        with torch.no_grad():
+            for k, gk in zip(self.names, grads):
+                self.m[k].mul_(b1).add_(gk, alpha=1 - b1)
+                self.v[k].mul_(b2).addcmul_(gk, gk, value=1 - b2)
+                V[k].sub_(lr_t * self.m[k] / (self.v[k].sqrt() + eps_a))
+        return float(loss)
+
+
 def synthetic_binarised(n, dim, seed=1, p=0.1307):
     """X[b,d] = 1{u < 0.1307}, labels b mod 10."""
     rng = np.random.RandomState(seed)
@@ -102,18 +149,30 @@ def synthetic_binarised(n, dim, seed=1, p=0.1307):
 
 
 def time_training(cfg: rg.GraphConfig, batch_size: int, n_steps: int, warmup: int, threads: int,
-                  seed_data=1, seed_w=0, seed_noise=2):
-    """Returns dict(samples_per_s, ms_per_step (median), p10, p90, cores)."""
+                  seed_data=1, seed_w=0, seed_noise=2, binarised=True, moe=None):
+    """Returns dict(samples_per_s, ms_per_step (median), p10, p90, cores).  moe = dict(n_experts, output_dim): the
+    `dmoe` step (MoeCpuTrainer) instead of the VAE step."""
     torch.set_num_threads(threads)
     n = batch_size * (n_steps + warmup)
-    X, y = synthetic_binarised(n, cfg.input_dim, seed_data)
+    if binarised:
+        X, y = synthetic_binarised(n, cfg.input_dim, seed_data)
+    else:                                            # CIFAR-shaped soft targets (includes/utils.py:204-210)
+        rng = np.random.RandomState(seed_data)
+        X = (rng.randint(0, 256, size=(n, cfg.input_dim)) / 255.0).astype(np.float32)
+        y = (np.arange(n) % 10).astype(np.int32)
     data = Dataset((X, y), batch_size=batch_size, shuffle=True)
-    tr = CpuTrainer(cfg, rg.init_variables(cfg, seed_w), seed=seed_noise)
+    if moe is None:
+        tr = CpuTrainer(cfg, rg.init_variables(cfg, seed_w), seed=seed_noise)
+        do_step = lambda b, lo: tr.step(b)
+    else:
+        tr = MoeCpuTrainer(cfg, rg.init_variables(cfg, seed_w), moe["n_experts"], moe["output_dim"], seed=seed_noise)
+        onehot = np.eye(moe["output_dim"], dtype=np.float32)
+        do_step = lambda b, lo: tr.step(b, onehot[(np.arange(lo, lo + len(b)) % moe["output_dim"])])
     times = []
     it = data.get_batches()
     t_prev = time.perf_counter()
     for i, batch in enumerate(it):
-        tr.step(batch)
+        do_step(batch, i * batch_size)
         t_now = time.perf_counter()
         if i >= warmup:
             times.append(t_now - t_prev)      # includes the Python batching of this batch
