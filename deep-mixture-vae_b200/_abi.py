@@ -14,7 +14,7 @@ _lib = None
 
 # enums (include/dmvae_b200.h)
 F32, BF16, U8 = 0, 1, 2
-ACT_NONE, ACT_RELU = 0, 1
+ACT_NONE, ACT_RELU, ACT_SIGMOID = 0, 1, 2
 INPUT_BINARY, INPUT_REAL = 0, 1
 MODE_DMVAE, MODE_DMVAE_SAMPLED, MODE_VADE = 0, 1, 2
 
@@ -119,10 +119,14 @@ SIGNATURES = {
     "dmvae_argmax_contingency": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_int, c_void_p,
                                          c_void_p, c_void_p]),
     "dmvae_dp_reduce_adam": (c_int, [c_void_p, c_int, c_int, C.POINTER(c_void_p), C.POINTER(c_void_p),
-                                     C.POINTER(c_void_p), c_void_p, c_void_p, c_int64, c_int64, c_int64, c_float, c_void_p,
-                                     c_float, c_float, c_float, c_int, c_void_p]),
+                                     C.POINTER(c_void_p), C.POINTER(c_void_p), C.POINTER(c_int64), c_int, c_void_p, c_void_p,
+                                     c_int64, c_int64, c_int64, c_float, c_void_p, c_float, c_float, c_float, c_int, c_void_p]),
     "dmvae_dp_reduce_adam_mc": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64,
                                         c_int64, c_float, c_void_p, c_float, c_float, c_float, c_void_p]),
+    "dmvae_dp_alloc": (c_int, [c_void_p, c_int64, C.POINTER(c_void_p), c_void_p]),
+    "dmvae_dp_open": (c_int, [c_void_p, c_void_p, C.POINTER(c_void_p)]),
+    "dmvae_dp_close": (c_int, [c_void_p, c_void_p]),
+    "dmvae_dp_free": (c_int, [c_void_p, c_void_p]),
     "dmvae_dp_barrier": (c_int, [c_void_p, c_int, c_int, C.POINTER(c_void_p), c_void_p, c_int, c_void_p]),
     "dmvae_zero_f32": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "dmvae_cast_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),

@@ -163,6 +163,15 @@ class VAE:
         eng = self._ensure_engine(session)
         names = [f.name for f in fetches]
         fd = {k.name: v for k, v in feed.items() if k.owner is self}
+        if "X" not in fd and "Z" in fd:
+            # generation: the latent code is fed directly (includes/visualization.py:83-87) - decoder only
+            bad = [n for n in names if n not in ("decoded_X", "reconstructed_X", "Z")]
+            if bad:
+                raise ValueError("with Z fed only decoded_X / reconstructed_X can be fetched (got %r)" % bad)
+            Zd = _to_device(fd["Z"], eng.device, torch.float32).contiguous()
+            rows = len(Zd)
+            eng.decode_latent(Zd, rows)
+            return [self._fetch(eng, n, rows) for n in names]
         if "X" not in fd:
             raise ValueError("feed_dict must contain the X placeholder")
         X = fd["X"]
@@ -206,13 +215,25 @@ class VAE:
         t = {"mean": lambda: eng.zh[:rows, :L], "log_var": lambda: eng.zh[:rows, L:2 * L],
              "logits": lambda: eng.ch[:rows, :K], "cluster_probs": lambda: eng.qc[:rows],
              "Z": lambda: eng.zb[:rows, :L], "decoded_X": lambda: eng.decoded[:rows, :D],
-             "reconstructed_X": lambda: eng.decoded[:rows, :D]}.get(name)
+             # base_models.py:295-300: sigmoid(decoded_X) for binary inputs - the output layer's GEMM with the sigmoid in
+             # its epilogue (DMVAE_ACT_SIGMOID), computed on demand
+             "reconstructed_X": lambda: eng.reconstruct(rows)[:rows, :D]}.get(name)
         if t is None:
             raise KeyError("cannot fetch %r" % name)
-        a = t().float().cpu().numpy()
-        if name == "reconstructed_X" and self.input_type == "binary":
-            a = 1.0 / (1.0 + np.exp(-a))                                  # base_models.py:295-296 (plots only)
-        return a
+        return t().float().cpu().numpy()
+
+    def decode(self, session, Z):
+        """Decoder only: reconstructed_X for given latent codes (what includes/visualization.py:83-87 does by feeding
+        ``model.Z``)."""
+        return session.run(self.reconstructed_X, feed_dict={self.Z: Z})
+
+    def reconstruct(self, session, X):
+        """reconstructed_X with zero noise (includes/visualization.py:39-46)."""
+        eps = self.epsilon if getattr(self, "epsilon", None) is not None else None
+        feed = {self.X: X}
+        if eps is not None:
+            feed[eps] = np.zeros((len(X), self.latent_dim), np.float32)
+        return session.run(self.reconstructed_X, feed_dict=feed)
 
     def train_op(self, session, data, kl_ratio=1.0):
         """base_models.py:112-132: one epoch; returns the mean batch loss.
@@ -238,7 +259,8 @@ class VAE:
         opt = eng.optimizer(key, self._lr[key])
         data.begin_epoch()                                     # draws the epoch's permutation (utils.py:450-454)
         runner = eng.dp if eng.dp is not None else eng
-        return runner.run_epoch(data.host_tensor(), data.batch_size, opt, kl_ratio, mode, perm=data.perm)
+        return runner.run_epoch(data.host_tensor(), data.batch_size, opt, kl_ratio, mode, perm=data.perm,
+                                while_busy=data.prefetch_epoch)
 
     def debug(self, session, data):
         """base_models.py:134-147 drops into pdb; here the prepared feed is returned instead."""

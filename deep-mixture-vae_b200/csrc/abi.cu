@@ -440,8 +440,11 @@ extern "C" int dmvae_step_tick(dmvae_ctx* ctx, void* state_dev, float lr, float 
 // ---------------------------------------------------------------------------------------------
 struct DpPeers {
   float* grads[8];
-  float* params[8];
+  float* params[8];          // fp32 master of each replica, or NULL: that replica keeps no master for this shard ...
+  float* params_rep[8];      // ... except inside the replicated ranges below (prior tables, logits layer)
   __nv_bfloat16* pbf[8];
+  int64_t rep_lo4[4], rep_hi4[4];   // float4 index ranges whose fp32 master every replica needs
+  int n_rep;
 };
 
 // WORLD > 0: compile-time rank count - the peer loads are unrolled and issued in groups of up to GROUP before the first
@@ -494,8 +497,12 @@ dp_reduce_adam_kernel(DpPeers peers, int rank, int world_rt, float* __restrict__
     reinterpret_cast<float4*>(v)[li] = vv;
     __nv_bfloat162 lo = __floats2bfloat162_rn(p.x, p.y), hi = __floats2bfloat162_rn(p.z, p.w);
     uint2 w = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+    bool rep = false;
+    for (int q = 0; q < peers.n_rep; ++q) rep = rep || (i >= peers.rep_lo4[q] && i < peers.rep_hi4[q]);
     for (int r = 0; r < world; ++r) {
-      if (peers.params[r]) reinterpret_cast<float4*>(peers.params[r])[i] = p;    // NULL: fp32 master kept by its owner only
+      float* pp = peers.params[r];                                               // NULL: fp32 master kept by its owner only,
+      if (!pp && rep) pp = peers.params_rep[r];                                  // except in the replicated ranges
+      if (pp) reinterpret_cast<float4*>(pp)[i] = p;
       if (peers.pbf[r]) reinterpret_cast<uint2*>(peers.pbf[r])[i] = w;
     }
   }
@@ -619,8 +626,54 @@ extern "C" int dmvae_dp_barrier(dmvae_ctx* ctx, int rank, int world, uint32_t* c
   return DMVAE_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// peer-mapped buffers through CUDA IPC (data parallel without torch: include/dmvae_b200.h)
+// ---------------------------------------------------------------------------------------------
+static_assert(sizeof(cudaIpcMemHandle_t) <= sizeof(dmvae_ipc_handle), "IPC handle does not fit");
+
+extern "C" int dmvae_dp_alloc(dmvae_ctx* ctx, int64_t bytes, void** local_ptr, dmvae_ipc_handle* handle_out) {
+  DMVAE_CHECK_ARG(ctx && local_ptr && handle_out && bytes > 0, "dmvae_dp_alloc: bad arguments");
+  DMVAE_CUDA(cudaSetDevice(ctx->device));
+  void* p = nullptr;
+  DMVAE_CUDA(cudaMalloc(&p, (size_t)bytes));
+  DMVAE_CUDA(cudaMemset(p, 0, (size_t)bytes));
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) {
+    cudaFree(p);
+    dmvae_set_error("dmvae_dp_alloc: cudaIpcGetMemHandle failed: %s", cudaGetErrorString(e));
+    return DMVAE_ERR_CUDA;
+  }
+  memset(handle_out, 0, sizeof(*handle_out));
+  memcpy(handle_out->bytes, &h, sizeof(h));
+  *local_ptr = p;
+  return DMVAE_OK;
+}
+
+extern "C" int dmvae_dp_open(dmvae_ctx* ctx, const dmvae_ipc_handle* peer_handle, void** peer_ptr) {
+  DMVAE_CHECK_ARG(ctx && peer_handle && peer_ptr, "dmvae_dp_open: NULL argument");
+  DMVAE_CUDA(cudaSetDevice(ctx->device));
+  cudaIpcMemHandle_t h;
+  memcpy(&h, peer_handle->bytes, sizeof(h));
+  DMVAE_CUDA(cudaIpcOpenMemHandle(peer_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return DMVAE_OK;
+}
+
+extern "C" int dmvae_dp_close(dmvae_ctx* ctx, void* peer_ptr) {
+  DMVAE_CHECK_ARG(ctx && peer_ptr, "dmvae_dp_close: NULL argument");
+  DMVAE_CUDA(cudaIpcCloseMemHandle(peer_ptr));
+  return DMVAE_OK;
+}
+
+extern "C" int dmvae_dp_free(dmvae_ctx* ctx, void* local_ptr) {
+  DMVAE_CHECK_ARG(ctx && local_ptr, "dmvae_dp_free: NULL argument");
+  DMVAE_CUDA(cudaFree(local_ptr));
+  return DMVAE_OK;
+}
+
 extern "C" int dmvae_dp_reduce_adam(dmvae_ctx* ctx, int rank, int world, float* const* grads_peers_host,
-                                    float* const* params_peers_host, void* const* params_bf16_peers_host, float* m,
+                                    float* const* params_peers_host, void* const* params_bf16_peers_host,
+                                    float* const* params_rep_peers_host, const int64_t* rep_ranges, int n_rep, float* m,
                                     float* v, int64_t n, int64_t shard_begin, int64_t shard_end, float lr_t,
                                     const float* lr_t_dev, float beta1, float beta2, float eps, int flags,
                                     void* stream) {
@@ -635,8 +688,17 @@ extern "C" int dmvae_dp_reduce_adam(dmvae_ctx* ctx, int rank, int world, float* 
     peers.grads[r] = grads_peers_host[r];
     peers.params[r] = params_peers_host[r];
     peers.pbf[r] = params_bf16_peers_host ? (__nv_bfloat16*)params_bf16_peers_host[r] : nullptr;
+    peers.params_rep[r] = params_rep_peers_host ? params_rep_peers_host[r] : nullptr;
     DMVAE_CHECK_ARG(peers.grads[r] && (peers.params[r] || (r != rank && peers.pbf[r])),
                     "dmvae_dp_reduce_adam: peer %d: gradient pointer, and fp32 or bf16 parameter pointer, required", r);
+  }
+  DMVAE_CHECK_ARG(n_rep >= 0 && n_rep <= 4 && (n_rep == 0 || (rep_ranges && params_rep_peers_host)),
+                  "dmvae_dp_reduce_adam: at most 4 replicated ranges, with their pointers");
+  peers.n_rep = n_rep;
+  for (int q = 0; q < n_rep; ++q) {
+    DMVAE_CHECK_ARG(rep_ranges[2 * q] % 4 == 0 && rep_ranges[2 * q + 1] % 4 == 0, "dmvae_dp_reduce_adam: replicated ranges must be 4-aligned");
+    peers.rep_lo4[q] = rep_ranges[2 * q] / 4;
+    peers.rep_hi4[q] = rep_ranges[2 * q + 1] / 4;
   }
   if (shard_end == shard_begin) return DMVAE_OK;
   DMVAE_CHECK_ARG((flags & ~(DMVAE_ADAM_ZERO_GRADS | DMVAE_ADAM_BACKGROUND)) == 0, "dmvae_dp_reduce_adam: unknown flags %d", flags);

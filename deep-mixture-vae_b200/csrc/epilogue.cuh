@@ -37,6 +37,7 @@ __device__ __forceinline__ float epi_apply(const EpiParams& ep, int n, float acc
   float v = acc;
   if (ep.bias && first) v += __ldg(ep.bias + n);
   if (ep.act == DMVAE_ACT_RELU) v = fmaxf(v, 0.f);
+  else if (ep.act == DMVAE_ACT_SIGMOID) v = 1.f / (1.f + __expf(-v));
   v = maskval > 0.f ? v : 0.f;
   if (ep.n_valid < ep.n_block) {
     int jb = n % ep.n_block;

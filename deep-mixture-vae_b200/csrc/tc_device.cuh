@@ -284,6 +284,10 @@ __device__ __forceinline__ void epilogue_warp_cols(uint32_t taddr, int col_begin
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
       }
+      if (!RELU && !MASK && ep.act == DMVAE_ACT_SIGMOID) {          // reconstructed_X = sigmoid(decoded_X), base_models.py:295-296
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __fdividef(1.f, 1.f + __expf(-v[j]));
+      }
       if (padded) {
         const int jb = n % ep.n_block;                    // n_block % 32 == 0: the chunk stays inside one block
         if (jb + 32 > ep.n_valid) {                       // the chunk touches the ones / zero padding columns

@@ -138,6 +138,9 @@ class DataParallel:
         self.master_sharded = eng.params_op is not None
         self._p_ptrs = VP(*[(p if (r == self.rank or not self.master_sharded) else None) for r, p in enumerate(ptrs)])
         self._p_ptrs_full = VP(*ptrs)                     # every replica's fp32 master (prior tables: read by the ELBO kernel)
+        rr = eng.layout.replicated_master_ranges()
+        self._n_rep = len(rr)
+        self._rep_ranges = (C.c_int64 * (2 * len(rr)))(*[x for lo_hi in rr for x in lo_hi])
         self._b_ptrs = VP(*[(p + 8 * P) if eng.params_op is not None else 0 for p in ptrs])
         self._pad_ptrs = VP(*[p + pad_off for p in ptrs])
         # NVSwitch multicast mapping of the same buffer (0 when the fabric / driver does not offer it)
@@ -235,35 +238,36 @@ class DataParallel:
             m, v = self._opt_shard_state(opt, ridx)
             # Some ranges need their fp32 master on EVERY rank even when the rest of the master is kept by its owner only
             # (Layout.replicated_master_ranges: the prior tables, read in fp32 by the fused ELBO kernel, and the logits
-            # layer, whose split bf16 operand copy is rebuilt from the master): the parts of the shard that overlap them
-            # are exchanged with all fp32 peer pointers set.
-            pieces, pos = [], b
-            for lo, hi in (eng.layout.replicated_master_ranges() if self.master_sharded else []):
-                lo, hi = max(lo, b), min(hi, e)
-                if hi <= lo:
-                    continue
-                if lo > pos:
-                    pieces.append((pos, lo, False))
-                pieces.append((lo, hi, True))
-                pos = hi
-            if pos < e:
-                pieces.append((pos, e, False))
-            for pb, pe, full in pieces:
-                if pe <= pb:
-                    continue
-                mo, vo = m.data_ptr() + 4 * (pb - b), v.data_ptr() + 4 * (pb - b)
-                if getattr(self, "_mc", 0) and not background:
-                    # in-switch reduction + broadcast store (NVLS); the fp32 master is broadcast only when it is replicated
-                    mc = self._mc
+            # layer, whose split bf16 operand copy is rebuilt from the master): the kernel writes the fp32 values of those
+            # ranges into every replica (one launch for the whole shard).
+            if getattr(self, "_mc", 0) and not background:
+                # in-switch reduction + broadcast store (NVLS): the multicast fp32 store is per launch, so the shard is
+                # cut at the replicated ranges
+                pieces, pos = [], b
+                for lo, hi in (eng.layout.replicated_master_ranges() if self.master_sharded else []):
+                    lo, hi = max(lo, b), min(hi, e)
+                    if hi <= lo:
+                        continue
+                    if lo > pos:
+                        pieces.append((pos, lo, False))
+                    pieces.append((lo, hi, True))
+                    pos = hi
+                if pos < e:
+                    pieces.append((pos, e, False))
+                mc = self._mc
+                for pb, pe, full in pieces:
                     abi.check(eng.lib.dmvae_dp_reduce_adam_mc(
                         eng.ctx, mc + self._mc_off[0], mc if (full or not self.master_sharded) else None,
-                        (mc + self._mc_off[1]) if eng.params_op is not None else None, eng.params.data_ptr(), mo, vo,
-                        eng.n_params, pb, pe, lr_t, lr_dev, opt.beta1, opt.beta2, opt.eps, eng._stream()))
-                    continue
-                abi.check(eng.lib.dmvae_dp_reduce_adam(eng.ctx, self.rank, self.world, self._g_ptrs,
-                                                       self._p_ptrs_full if full else self._p_ptrs, self._b_ptrs, mo, vo,
-                                                       eng.n_params, pb, pe, lr_t, lr_dev, opt.beta1, opt.beta2, opt.eps,
-                                                       2 if background else 0, eng._stream()))
+                        (mc + self._mc_off[1]) if eng.params_op is not None else None, eng.params.data_ptr(),
+                        m.data_ptr() + 4 * (pb - b), v.data_ptr() + 4 * (pb - b), eng.n_params, pb, pe, lr_t, lr_dev,
+                        opt.beta1, opt.beta2, opt.eps, eng._stream()))
+                continue
+            abi.check(eng.lib.dmvae_dp_reduce_adam(eng.ctx, self.rank, self.world, self._g_ptrs, self._p_ptrs, self._b_ptrs,
+                                                   self._p_ptrs_full if self.master_sharded else None,
+                                                   self._rep_ranges if self.master_sharded else None,
+                                                   self._n_rep if self.master_sharded else 0, m.data_ptr(), v.data_ptr(),
+                                                   eng.n_params, b, e, lr_t, lr_dev, opt.beta1, opt.beta2, opt.eps,
+                                                   2 if background else 0, eng._stream()))
         self._barrier(ch + 1)                             # every replica updated, every gradient shard consumed
         eng._refresh_split_heads()                        # logits layer: hi | lo | lo2 operand copy from the (replicated) master
         # clear the local gradients of these ranges (split-K accumulates into them): local HBM, not 7/8 remote stores
@@ -345,9 +349,9 @@ class DataParallel:
     def train_step(self, X, rows, opt, kl_ratio=1.0):
         self.eng.train_step(X, rows, opt, kl_ratio=kl_ratio)
 
-    def run_epoch(self, host, batch_size, opt, kl_ratio=1.0, mode="all", max_steps=None, perm=None):
+    def run_epoch(self, host, batch_size, opt, kl_ratio=1.0, mode="all", max_steps=None, perm=None, while_busy=None):
         """Every rank iterates over ITS host shard; the returned loss is the global mean (one all-reduce per epoch)."""
-        loss = self.eng.run_epoch(host, batch_size, opt, kl_ratio, mode, max_steps, perm)
+        loss = self.eng.run_epoch(host, batch_size, opt, kl_ratio, mode, max_steps, perm, while_busy)
         t = torch.tensor([loss], dtype=torch.float64, device=self.eng.device)
         dist.all_reduce(t, group=self.group)
         return float(t[0])

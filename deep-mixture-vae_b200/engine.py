@@ -803,6 +803,28 @@ class Engine:
             a = self.act[nm]
         self._fwd("decx", a, a.stride(0), self.decoded, self.dec_dt, _abi.ACT_NONE, rows)
 
+    def reconstruct(self, rows: int) -> torch.Tensor:
+        """reconstructed_X (base_models.py:295-300) of the rows last decoded: the output layer once more with the sigmoid
+        in the GEMM epilogue (binary inputs; identity for real-valued ones).  Returns the device buffer [rows, >= D]."""
+        if self.input_type != "binary":
+            return self.decoded
+        if getattr(self, "recon", None) is None or self.recon.shape[0] < self.max_rows:
+            self.recon = torch.zeros_like(self.decoded)
+        a = self.act[self.dec_chain[-1]]
+        self._fwd("decx", a, a.stride(0), self.recon, self.dec_dt, _abi.ACT_SIGMOID, rows)
+        return self.recon
+
+    def decode_latent(self, Z: torch.Tensor, rows: int):
+        """Generation entry point (includes/visualization.py:83-87 feeds model.Z directly): Z [rows, L] fp32 on the device
+        -> decoder -> decoded_X logits in self.decoded."""
+        if rows > self.max_rows:
+            self._alloc_activations(rows)
+        if getattr(self, "_params_dirty", False):
+            self.sync_operand_copy()
+        _abi.check(self.lib.dmvae_stage_features(self.ctx, Z.data_ptr(), Z.stride(0), rows, self.L, 0, self.zb.data_ptr(),
+                                                 self.dt, self.zb.stride(0), self.zb.shape[1], self._stream()))
+        self.decode(rows)
+
     # ------------------------------------------------------------------------------------------
     # chained forward: encoder -> heads (+ fused reparameterisation) -> decoder in ONE persistent launch
     # ------------------------------------------------------------------------------------------
@@ -1392,7 +1414,7 @@ class Engine:
         self._graph_replay_launches += n_nodes
 
     def run_epoch(self, host: torch.Tensor, batch_size: int, opt: AdamState, kl_ratio: float = 1.0, mode: str = "all",
-                  max_steps: Optional[int] = None, perm: Optional[np.ndarray] = None) -> float:
+                  max_steps: Optional[int] = None, perm: Optional[np.ndarray] = None, while_busy=None) -> float:
         """One pass over a (pinned) host array [N, D].  Per step, on a copy stream and double-buffered so that it overlaps
         the previous step: the batch's rows cross the bus into a staging buffer - a plain asynchronous copy of a
         contiguous slice, or with ``perm`` (the epoch's shuffle, includes/utils.py:450-454) a gather kernel that reads the
@@ -1454,12 +1476,14 @@ class Engine:
             self._loss_log[i].copy_(self.loss_out, non_blocking=True)
             self._free[b].record(cur)
         self._loss_host[:nb].copy_(self._loss_log[:nb], non_blocking=True)
+        if while_busy is not None:
+            while_busy()                           # host work hidden behind the queued steps (e.g. the next epoch's shuffle)
         cur.synchronize()
         col = {"all": 3, "vae": 0, "prior": 3}[mode]
         return float(self._loss_host[:nb, col].sum()) / nb
 
     def run_epoch_moe(self, host_x: torch.Tensor, host_y: torch.Tensor, batch_size: int, opt: AdamState, kl_ratio: float = 1.0,
-                      perm: Optional[np.ndarray] = None, max_steps: Optional[int] = None) -> np.ndarray:
+                      perm: Optional[np.ndarray] = None, max_steps: Optional[int] = None, while_busy=None) -> np.ndarray:
         """One pass of the MoE training step (models.py:194-221) over pinned host arrays X [N, D] / Y [N, O], batches staged
         like run_epoch.  Returns per-step [supervised loss sum, error sum, recon, KL_c, KL_z, VAE loss] as a host array."""
         N = host_x.shape[0]
@@ -1515,6 +1539,8 @@ class Engine:
             self._moe_log[i, 2:].copy_(self.loss_out, non_blocking=True)
             self._free[b].record(cur)
         self._moe_log_host[:nb].copy_(self._moe_log[:nb], non_blocking=True)
+        if while_busy is not None:
+            while_busy()
         cur.synchronize()
         return self._moe_log_host[:nb].numpy().copy()
 

@@ -185,7 +185,15 @@ class Dataset:
             self._permute()
 
     def _permute(self):
-        self.perm = np.random.permutation(len(self.data))
+        nxt = getattr(self, "_next_perm", None)
+        self._next_perm = None
+        self.perm = nxt if nxt is not None else np.random.permutation(len(self.data))
+
+    def prefetch_epoch(self):
+        """Draw the NEXT epoch's permutation now (same generator, same order of draws): the fast training path calls
+        this while the device is still working through the current epoch, so the draw costs no device time."""
+        if self.shuffle and getattr(self, "_next_perm", None) is None:
+            self._next_perm = np.random.permutation(len(self.data))
 
     def host_tensor(self) -> torch.Tensor:
         """Pinned host copy in storage dtype (uint8 for binarised data), rows in their ORIGINAL order; built once."""
@@ -238,7 +246,13 @@ class MEDataset:
 
     def begin_epoch(self):
         if self.shuffle:
-            self.perm = np.random.permutation(len(self.data))
+            nxt = getattr(self, "_next_perm", None)
+            self._next_perm = None
+            self.perm = nxt if nxt is not None else np.random.permutation(len(self.data))
+
+    def prefetch_epoch(self):
+        if self.shuffle and getattr(self, "_next_perm", None) is None:
+            self._next_perm = np.random.permutation(len(self.data))
 
     def get_batches(self):
         self.begin_epoch()

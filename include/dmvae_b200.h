@@ -44,7 +44,7 @@ enum dmvae_status {
 };
 
 enum dmvae_dtype { DMVAE_F32 = 0, DMVAE_BF16 = 1, DMVAE_U8 = 2 };
-enum dmvae_act { DMVAE_ACT_NONE = 0, DMVAE_ACT_RELU = 1 };
+enum dmvae_act { DMVAE_ACT_NONE = 0, DMVAE_ACT_RELU = 1, DMVAE_ACT_SIGMOID = 2 /* reconstructed_X, base_models.py:295-296 */ };
 enum dmvae_input_type { DMVAE_INPUT_BINARY = 0, DMVAE_INPUT_REAL = 1 };   /* base_models.py:72-85 */
 enum dmvae_elbo_mode {
   DMVAE_MODE_DMVAE = 0,          /* cluster_sample=False, w = softmax(logits)   priors.py:130-145 */
@@ -264,6 +264,11 @@ int dmvae_argmax_contingency(dmvae_ctx* ctx, const float* scores, int64_t ld, in
  * shard it consumed in every replica.  The caller brackets the launch with a cross-rank barrier on each side. */
 int dmvae_dp_reduce_adam(dmvae_ctx* ctx, int rank, int world, float* const* grads_peers_host,
                          float* const* params_peers_host, void* const* params_bf16_peers_host,
+                         float* const* params_rep_peers_host /* every replica's fp32 master, or NULL */,
+                         const int64_t* rep_ranges /* [2 n_rep] float index ranges [lo, hi) whose fp32 master is written into
+                                                      EVERY replica even where params_peers_host[r] is NULL (prior tables: read in
+                                                      fp32 by the ELBO kernel; logits layer: dmvae_split3_bf16 needs the master) */,
+                         int n_rep,
                          float* m, float* v, int64_t n, int64_t shard_begin, int64_t shard_end,
                          float lr_t, const float* lr_t_dev, float beta1, float beta2, float eps,
                          int flags /* DMVAE_ADAM_ZERO_GRADS: clear the consumed shard in every replica (0: every rank clears its
@@ -283,6 +288,17 @@ int dmvae_dp_reduce_adam_mc(dmvae_ctx* ctx, const float* mc_grads, float* mc_par
 #define DMVAE_DP_CHANNELS 32
 int dmvae_dp_barrier(dmvae_ctx* ctx, int rank, int world, uint32_t* const* pads_host, uint32_t* epochs, int channel,
                      void* stream);
+/* Peer-mapped buffers WITHOUT torch (one process per GPU): allocate the flat parameter / gradient buffer with
+ * dmvae_dp_alloc, send the 64-byte handle to the other ranks over whatever the host has (a file, a socket, MPI), map the
+ * peers' buffers with dmvae_dp_open, and pass the pointers to dmvae_dp_reduce_adam / dmvae_dp_barrier.  (The Python host
+ * of this repository uses torch.distributed's symmetric memory for the same purpose.)  CUDA IPC under the hood: the
+ * buffers are NVLink peer-mapped on a single node. */
+typedef struct dmvae_ipc_handle { unsigned char bytes[64]; } dmvae_ipc_handle;
+int dmvae_dp_alloc(dmvae_ctx* ctx, int64_t bytes, void** local_ptr, dmvae_ipc_handle* handle_out);
+int dmvae_dp_open(dmvae_ctx* ctx, const dmvae_ipc_handle* peer_handle, void** peer_ptr);
+int dmvae_dp_close(dmvae_ctx* ctx, void* peer_ptr);
+int dmvae_dp_free(dmvae_ctx* ctx, void* local_ptr);
+
 /* params_peers_host[r] may be NULL for r != rank when params_bf16_peers_host[r] is given: the fp32 master copy of a
  * shard then lives on its owner only (the bf16 operand copy, which is all the GEMMs read, is still replicated). */
 /* zero a fp32 buffer (gradient accumulators) */

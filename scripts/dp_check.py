@@ -90,7 +90,17 @@ def main():
     gops = [torch.zeros_like(ops) for _ in range(world)]
     dist.all_gather(gops, ops)
     same = all(torch.equal(gathered[0], g) for g in gathered) and all(torch.equal(gops[0], g) for g in gops)
-    cast_ok = torch.equal(eng.params.to(torch.bfloat16).float(), ops)       # full master (after the gather) == operand copy
+    # full master (after the gather) == operand copy, except the logits layer, whose operand copy holds hi | lo | lo2
+    ly = eng.layers["ch"]
+    mask = torch.ones_like(ops, dtype=torch.bool)
+    mask[ly.offset: ly.offset + ly.size] = False
+    cast = eng.params.to(torch.bfloat16).float()
+    chm = eng.params[ly.offset: ly.offset + ly.size].view(ly.in_pad, ly.out_pad)
+    cho = ops[ly.offset: ly.offset + ly.size].view(ly.in_pad, ly.out_pad)
+    hi = chm[:, :eng.K].to(torch.bfloat16).float()
+    lo = (chm[:, :eng.K] - hi).to(torch.bfloat16).float()
+    split_ok = torch.equal(cho[:, :eng.K], hi) and torch.equal(cho[:, eng.Kc: eng.Kc + eng.K], lo)
+    cast_ok = torch.equal(cast[mask], ops[mask]) and split_ok
     moved = float((mine - torch.tensor(np.concatenate([make("bf16", Bl).get_variable(n).ravel() for n in names]), device="cuda")).abs().max())
     good = bool(same and cast_ok and dp.master_sharded and moved > 1e-4)
     ok = ok and good

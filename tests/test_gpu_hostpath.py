@@ -189,3 +189,34 @@ def test_train_main_runs_one_epoch(argv, tmp_path, monkeypatch):
     model = argv[1]
     assert os.path.exists(tmp_path / (model + "_logs.txt"))
     assert os.path.isdir(tmp_path / "saved-models")
+
+
+@pytest.mark.parametrize("gd,tol", [("fp32", 1e-5), ("bf16", 2e-2)])
+def test_decode_and_reconstruct_entry_points(gd, tol):
+    """includes/visualization.py:39-46 (reconstructed_X with zero noise) and :83-87 (model.Z fed directly): the sigmoid
+    is the output GEMM's epilogue (DMVAE_ACT_SIGMOID); both entry points against the oracle's reconstructed_X."""
+    from dmvae_b200.session import Session
+    X, _ = _clustered(300, seed=8)
+    cfg = rg.GraphConfig(model="dmvae", input_dim=784, latent_dim=10, n_classes=10)
+    V = rg.init_variables(cfg, 2)
+    m = _model(gd)
+    m.set_variables(V)
+    sess = Session()
+    eps0 = np.zeros((300, 10), np.float32)
+    out, _ = rg.loss_and_grads(cfg, V, X, eps0, dtype=torch.float32)
+    rec = m.reconstruct(sess, X)
+    assert rec.shape == (300, 784) and np.all((rec > 0) & (rec < 1))
+    assert np.abs(rec - out["reconstructed_X"]).max() < tol
+    dec = sess.run(m.decoded_X, feed_dict={m.X: X, m.epsilon: eps0})
+    assert relerr_(dec, out["decoded_X"]) < max(tol, 1e-4)
+    # generation: feed Z, fetch reconstructed_X
+    Z = np.asarray(out["Z"], np.float32)
+    gen = m.decode(sess, Z)
+    assert np.abs(gen - out["reconstructed_X"]).max() < tol
+    with pytest.raises(ValueError):
+        sess.run(m.logits, feed_dict={m.Z: Z})
+
+
+def relerr_(got, ref):
+    got, ref = np.asarray(got, np.float64), np.asarray(ref, np.float64)
+    return float(np.abs(got - ref).max() / max(np.abs(ref).max(), 1e-30))

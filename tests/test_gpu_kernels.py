@@ -439,7 +439,7 @@ def test_adam_launch_shapes_and_exchange_kernel_agree(lib, ctx):
         else:                                    # exchange kernel, one rank: its own buffers are the only "peers"
             VP = C.c_void_p * 1
             _abi.check(lib.dmvae_dp_reduce_adam(ctx, 0, 1, VP(gr.data_ptr()), VP(p.data_ptr()), VP(pb.data_ptr()),
-                                                m.data_ptr(), v.data_ptr(), n, 0, n, 1.5e-3, None, 0.9, 0.999, 1e-8,
+                                                None, None, 0, m.data_ptr(), v.data_ptr(), n, 0, n, 1.5e-3, None, 0.9, 0.999, 1e-8,
                                                 1 | (2 if kind == "dp_bg" else 0), stream()))
         torch.cuda.synchronize()
         return [t.clone() for t in (p, m, v, pb, gr)]
