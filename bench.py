@@ -134,7 +134,10 @@ def make_dataset(cfg, n_rows, B, seed):
     if cfg["model"] == "dmoe":
         Y = np.eye(cfg["output_dim"], dtype=np.float32)[cls % cfg["output_dim"]]
         return MEDataset((X, cls, Y), batch_size=B)
-    return Dataset((X.astype(np.float32) if not cfg["binarised"] else X, cls), batch_size=B)
+    if not cfg["binarised"]:
+        # what a user holds: float32 pixel intensities k/255; Dataset recognises the 8-bit grid and stores / ships bytes
+        X = X.astype(np.float32) * np.float32(1.0 / 255.0)
+    return Dataset((X, cls), batch_size=B)
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -256,9 +259,9 @@ def run_ours(args):
         from dmvae_b200.dp import DataParallel
         dp = DataParallel(eng, mode=args.dp_mode)
     opt = eng.optimizer("moe" if is_moe else "train", 0.002)
-    xdtype = torch.uint8 if cfg["binarised"] else torch.float32
-    xdt = _abi.U8 if cfg["binarised"] else _abi.F32
-    row_bytes = cfg["D"] * (1 if cfg["binarised"] else 4)
+    xdtype, xdt = torch.uint8, _abi.U8                               # storage form: 0/1, or 8-bit intensities (x_scale 1/255)
+    row_bytes = cfg["D"]
+    eng.x_scale = CFG.x_scale(cfg)
     NB = max(2, min(16, int(260e6 // (B * row_bytes))))             # resident batches rotated through
     resident = torch.from_numpy(CFG.synth_inputs(cfg, NB * B, seed=1 + rank)).to(dev)
     xs = torch.empty(B, cfg["D"], dtype=xdtype, device=dev)          # static input buffer of the captured step
@@ -368,7 +371,7 @@ def run_ours(args):
         "adam_us": adam_us,
     }
     if elbo_us is not None:
-        eb = CFG.elbo_bytes_per_sample(cfg, 1 if cfg["binarised"] else 4, logit_bytes) * B
+        eb = CFG.elbo_bytes_per_sample(cfg, 1, logit_bytes) * B
         traffic = None
         tp = os.path.join(ROOT, "profiles", "r02_elbo_traffic.json")
         if os.path.exists(tp):
@@ -382,6 +385,8 @@ def run_ours(args):
                                           % (elbo_nrot, elbo_ws / 1e6)}
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(cfg, bounded_seconds=20.0)
+    if world == 1 and args.config == 2 and not args.no_also:
+        out["also"] = also_configs()
     print(json.dumps(out), flush=True)
     _finish(world, dev)
 
@@ -424,6 +429,25 @@ def cpu_baseline(cfg, bounded_seconds=20.0):
                       (r["steps"], batch, r["ms_per_step"], r["p10_ms"], r["p90_ms"])}
 
 
+def also_configs(ids=(3, 5, 4)):
+    """The other BASELINE.json configurations, each in a fresh process (short runs; the full line of each is
+    `python bench.py --config N`): step time, samples/s and the GEMM / ELBO roofline fractions."""
+    res = {}
+    for c in ids:
+        try:
+            p = subprocess.run([sys.executable, os.path.abspath(__file__), "--config", str(c), "--steps", "40", "--warmup", "5",
+                                "--no_cpu_baseline"], capture_output=True, text=True, timeout=300)
+            line = [ln for ln in p.stdout.splitlines() if ln.startswith("{")][-1]
+            d = json.loads(line)
+            res["cfg%d" % c] = {"workload": d["config"]["workload"], "ms_per_step": d["ms_per_step"], "value": d["value"],
+                                "e2e_ms_per_step": d["e2e"]["ms_per_step"], "gemm_frac": d["roofline"]["frac"],
+                                "gemm_step_frac": d["roofline"]["step_frac"],
+                                "elbo_frac": d.get("roofline_elbo", {}).get("frac")}
+        except Exception as ex:                     # never let the side measurements break the headline line
+            res["cfg%d" % c] = {"error": repr(ex)[:200]}
+    return res
+
+
 def run_reference(args):
     """Reference arm: the reference's own CPU implementation of the path cannot run (TensorFlow 1.x is not installable
     here), so this times the op-for-op CPU port in oracle/ on the same config, rank 0 only."""
@@ -462,6 +486,7 @@ def main():
     ap.add_argument("--gemm_dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--dp_mode", default="auto")
     ap.add_argument("--no_cpu_baseline", action="store_true")
+    ap.add_argument("--no_also", action="store_true", help="skip the short side runs of configs 3 / 4 / 5 (default config only)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

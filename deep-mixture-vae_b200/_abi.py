@@ -67,7 +67,7 @@ class ElboArgs(C.Structure):
                 ("d_logits", c_void_p), ("dlogits_dtype", c_int32), ("ld_dlogits", c_int64), ("dlogits_cols", c_int32),
                 ("d_Z_gamma", c_void_p), ("ld_dzg", c_int64),
                 ("w_scratch", c_void_p), ("f_scratch", c_void_p),
-                ("d_gate_extra", c_void_p), ("ld_dge", c_int64)]
+                ("d_gate_extra", c_void_p), ("ld_dge", c_int64), ("x_scale", c_float)]
 
 
 class MoeArgs(C.Structure):
@@ -99,7 +99,7 @@ SIGNATURES = {
                                    c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "dmvae_linear_wgrad": (c_int, [c_void_p, c_int, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64,
                                    c_int, c_int, c_int, c_int, c_int, c_void_p]),
-    "dmvae_stage_input": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_void_p, c_int, c_int64, c_int, c_int, c_void_p]),
+    "dmvae_stage_input": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_void_p, c_int, c_int64, c_int, c_int, c_float, c_void_p]),
     "dmvae_gather_rows": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p]),
     "dmvae_reparam_fwd": (c_int, [c_void_p, C.POINTER(ReparamArgs), c_void_p]),
     "dmvae_reparam_bwd": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p,

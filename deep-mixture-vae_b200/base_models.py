@@ -259,8 +259,9 @@ class VAE:
         opt = eng.optimizer(key, self._lr[key])
         data.begin_epoch()                                     # draws the epoch's permutation (utils.py:450-454)
         runner = eng.dp if eng.dp is not None else eng
-        return runner.run_epoch(data.host_tensor(), data.batch_size, opt, kl_ratio, mode, perm=data.perm,
-                                while_busy=data.prefetch_epoch)
+        host = data.host_tensor()
+        return runner.run_epoch(host, data.batch_size, opt, kl_ratio, mode, perm=data.perm,
+                                while_busy=data.prefetch_epoch, x_scale=data.host_scale)
 
     def debug(self, session, data):
         """base_models.py:134-147 drops into pdb; here the prepared feed is returned instead."""
@@ -385,6 +386,8 @@ class DeepMixtureVAE(VAE):
         # batches come from the dataset's pinned host copy (storage dtype: 1 byte / pixel for binarised data), staged
         # asynchronously into a persistent device buffer; rows stay in their original order, like data.classes
         host = data.host_tensor() if isinstance(data, Dataset) else None
+        if host is not None:
+            eng.x_scale = data.host_scale
         buf = None
         if host is not None:
             buf = getattr(eng, "_eval_stage", None)

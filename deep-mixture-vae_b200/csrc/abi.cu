@@ -185,7 +185,7 @@ extern "C" int dmvae_fold3(dmvae_ctx* ctx, float* Y, int64_t ld, int rows, int K
 // ---------------------------------------------------------------------------------------------
 template <typename TX, typename TO>
 __global__ void stage_input_kernel(const TX* __restrict__ X, int64_t ldx, TO* __restrict__ A, int64_t lda, int rows,
-                                   int D, int vec) {
+                                   int D, int vec, float xs) {
   pdl_wait();
   pdl_launch_dependents();
   // one warp per row; 8 elements per lane per iteration when the row pitches allow vector access
@@ -201,19 +201,24 @@ __global__ void stage_input_kernel(const TX* __restrict__ X, int64_t ldx, TO* __
       for (int j = lane * 8; j < Dv; j += 256) {
         float v[8];
         Vec8<TX>::load(x + j, v);
+        if (sizeof(TX) == 1) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] *= xs;
+        }
         Vec8<TO>::store(a + j, v);
       }
       j0 = Dv;
     }
     for (int j = j0 + lane; j < (int)lda; j += 32) {
-      float v = j < D ? to_f32<TX>(x[j]) : (j == D ? 1.f : 0.f);
+      float v = j < D ? to_f32<TX>(x[j]) * (sizeof(TX) == 1 ? xs : 1.f) : (j == D ? 1.f : 0.f);
       a[j] = from_f32<TO>(v);
     }
   }
 }
 
 extern "C" int dmvae_stage_input(dmvae_ctx* ctx, const void* X, int x_dtype, int64_t ldx, void* A0, int out_dtype,
-                                 int64_t ld_out, int rows, int D, void* stream) {
+                                 int64_t ld_out, int rows, int D, float x_scale, void* stream) {
+  const float xs = x_scale == 0.f ? 1.f : x_scale;
   DMVAE_CHECK_ARG(ctx && X && A0, "dmvae_stage_input: NULL pointer");
   DMVAE_CHECK_ARG(rows >= 0 && D > 0 && ldx >= D && ld_out > D, "dmvae_stage_input: need ldx >= D and ld_out > D");
   if (rows == 0) return DMVAE_OK;
@@ -221,7 +226,7 @@ extern "C" int dmvae_stage_input(dmvae_ctx* ctx, const void* X, int x_dtype, int
   cudaStream_t s = (cudaStream_t)stream;
   const int vec = (ldx % 8 == 0) && (ld_out % 8 == 0) && (((uintptr_t)X) % (8 * dmvae_dtype_size(x_dtype)) == 0) &&
                   (((uintptr_t)A0) % (8 * dmvae_dtype_size(out_dtype)) == 0);
-#define STAGE(TX, TO) dmvae_launch(stage_input_kernel<TX, TO>, dim3(blocks), dim3(256), 0, s, true, (const TX*)X, ldx, (TO*)A0, ld_out, rows, D, vec)
+#define STAGE(TX, TO) dmvae_launch(stage_input_kernel<TX, TO>, dim3(blocks), dim3(256), 0, s, true, (const TX*)X, ldx, (TO*)A0, ld_out, rows, D, vec, xs)
   if (x_dtype == DMVAE_F32 && out_dtype == DMVAE_F32) STAGE(float, float);
   else if (x_dtype == DMVAE_F32 && out_dtype == DMVAE_BF16) STAGE(float, __nv_bfloat16);
   else if (x_dtype == DMVAE_U8 && out_dtype == DMVAE_F32) STAGE(uint8_t, float);

@@ -23,6 +23,7 @@ constexpr float kEps0 = 1e-20f;
 
 struct ElboParams {
   dmvae_elbo_args a;
+  float xs, xo;    // uint8 targets: x = byte * xs; centred form x - 1/2 = fma(2^15 + byte, xs, xo), xo = -(2^15 xs + 1/2)
   int Ls;          // padded (odd) row stride of the shared prior tables
   int vec_ok;      // 8-wide vector path usable for the streaming part
   int bulk_ok;     // rows can be moved with 16-byte-granular bulk async copies (row-tile kernel)
@@ -45,6 +46,17 @@ __device__ __forceinline__ float recon1(float x, float d, float s, float& g) {
     return 0.5f * df * df;
   }
 }
+
+// uint8 targets carry `xs` per unit (1 for binarised data, 1/255 for 8-bit intensities); other dtypes are values already
+template <typename TX>
+__device__ __forceinline__ void scale8(float (&x)[8], float xs) {
+  if (sizeof(TX) == 1) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] *= xs;
+  }
+}
+template <typename TX>
+__device__ __forceinline__ float scale1(float x, float xs) { return sizeof(TX) == 1 ? x * xs : x; }
 
 template <int INPUT>
 __device__ __forceinline__ float recon8(const float (&x)[8], const float (&d)[8], float (&g)[8], float s) {
@@ -116,6 +128,8 @@ __global__ void __launch_bounds__(kThreads) elbo_kernel(const ElboParams p) {
         Vec8<TD>::load(dr + j, d0);
         Vec8<TX>::load(xr + j + 256, x1);
         Vec8<TD>::load(dr + j + 256, d1);
+        scale8<TX>(x0, p.xs);
+        scale8<TX>(x1, p.xs);
         racc += recon8<INPUT>(x0, d0, g0, s_rec);
         racc += recon8<INPUT>(x1, d1, g1, s_rec);
         Vec8<TD>::store(gr + j, g0);
@@ -125,13 +139,14 @@ __global__ void __launch_bounds__(kThreads) elbo_kernel(const ElboParams p) {
         float x0[8], d0[8], g0[8];
         Vec8<TX>::load(xr + j, x0);
         Vec8<TD>::load(dr + j, d0);
+        scale8<TX>(x0, p.xs);
         racc += recon8<INPUT>(x0, d0, g0, s_rec);
         Vec8<TD>::store(gr + j, g0);
       }
     } else {
       for (int j = lane; j < D; j += 32) {
         float g0;
-        racc += recon1<INPUT>(to_f32<TX>(xr[j]), to_f32<TD>(dr[j]), s_rec, g0);
+        racc += recon1<INPUT>(scale1<TX>(to_f32<TX>(xr[j]), p.xs), to_f32<TD>(dr[j]), s_rec, g0);
         gr[j] = from_f32<TD>(g0);
       }
     }
@@ -486,22 +501,24 @@ __device__ __forceinline__ float recon1_rt(float x, float d, float s, float& g) 
 
 // 8 targets of a shared-memory tile as floats, optionally centred (x - 0.5)
 template <typename T, bool CENTRED>
-__device__ __forceinline__ void tile8_x(uint32_t a, float (&x)[8]) {
+__device__ __forceinline__ void tile8_x(uint32_t a, float (&x)[8], float xs, float xo) {
   Tile8<T>::load(a, x);
+  scale8<T>(x, xs);
   if (CENTRED) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) x[i] -= 0.5f;
   }
 }
 template <>
-__device__ __forceinline__ void tile8_x<uint8_t, true>(uint32_t a, float (&x)[8]) {
+__device__ __forceinline__ void tile8_x<uint8_t, true>(uint32_t a, float (&x)[8], float xs, float xo) {
   uint32_t lo, hi;
   asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(lo), "=r"(hi) : "r"(a));
-  // byte b -> float bits 0x4700bb00 = 2^15 + b (ulp 2^-8), minus (2^15 + 0.5): b - 0.5 exactly; one PRMT + one FADD
+  // byte b -> float bits 0x4700bb00 = 2^15 + b (ulp 2^-8); fma(2^15 + b, xs, -(2^15 xs + 0.5)) = b xs - 0.5 with ONE rounding
+  // (exact for xs = 1): one PRMT + one FFMA per element whatever the scale
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    x[i] = __uint_as_float(__byte_perm(lo, 0x47000000u, 0x7504 | (i << 4))) - 32768.5f;
-    x[4 + i] = __uint_as_float(__byte_perm(hi, 0x47000000u, 0x7504 | (i << 4))) - 32768.5f;
+    x[i] = fmaf(__uint_as_float(__byte_perm(lo, 0x47000000u, 0x7504 | (i << 4))), xs, xo);
+    x[4 + i] = fmaf(__uint_as_float(__byte_perm(hi, 0x47000000u, 0x7504 | (i << 4))), xs, xo);
   }
 }
 
@@ -838,13 +855,14 @@ __global__ void __launch_bounds__(kFastThreads, 4) elbo_rowtile_kernel(const Elb
       if (FAST) {
         float x[8];
         uint32_t dw[4], gw[4];
-        tile8_x<TX, CENTRED>(xa, x);
+        tile8_x<TX, CENTRED>(xa, x, p.xs, p.xo);
         asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(dw[0]), "=r"(dw[1]), "=r"(dw[2]), "=r"(dw[3]) : "r"(da));
         recon8_t<INPUT, PRECISE>(x, dw, gw, s_rec, acc, prod);
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(da), "r"(gw[0]), "r"(gw[1]), "r"(gw[2]), "r"(gw[3]) : "memory");
       } else {
         float x[8], d[8], g[8];
         Tile8<TX>::load(xa, x);
+        scale8<TX>(x, p.xs);
         Tile8<TD>::load(da, d);
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc += recon1_rt<INPUT>(x[i], d[i], s_rec, g[i]);
@@ -1130,6 +1148,8 @@ extern "C" int dmvae_elbo_fwd_bwd(dmvae_ctx* ctx, const dmvae_elbo_args* a, void
   if (a->rows == 0) return DMVAE_OK;
   ElboParams p;
   p.a = *a;
+  p.xs = a->x_scale == 0.f ? 1.f : a->x_scale;
+  p.xo = -(32768.f * p.xs + 0.5f);
   p.Ls = a->L | 1;
   const size_t xs = dmvae_dtype_size(a->x_dtype), ds = dmvae_dtype_size(a->dec_dtype);
   p.vec_ok = (a->D % 8 == 0) && (a->ldx % 8 == 0) && (a->ld_dec % 8 == 0) && (a->ld_ddec % 8 == 0) &&

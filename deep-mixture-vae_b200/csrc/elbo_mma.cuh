@@ -473,9 +473,12 @@ __global__ void __launch_bounds__(kLatThreadsM, 1) elbo_latent_mma_kernel(const 
 // Writes d_decoded (padding columns zeroed), per_sample.x = R and per_sample.w = recon_scale R + r (C + Zk).
 // ---------------------------------------------------------------------------------------------------------------
 template <typename TX, bool CENTRED>
-__device__ __forceinline__ void gload8_x(const TX* p, float (&x)[8]) {
+__device__ __forceinline__ void gload8_x(const TX* p, float (&x)[8], float xs) {
   Vec8<TX>::load(p, x);
-  if (CENTRED) {
+  if (sizeof(TX) == 1) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] = CENTRED ? fmaf(x[i], xs, -0.5f) : x[i] * xs;
+  } else if (CENTRED) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) x[i] -= 0.5f;
   }
@@ -504,10 +507,10 @@ __global__ void __launch_bounds__(256) elbo_recon_kernel(const ElboParams p) {
           float x0[8], x1[8];
           uint4 d0, d1 = make_uint4(0u, 0u, 0u, 0u);
           const bool two = j + 256 < D;
-          gload8_x<TX, CENTRED>(xr + j, x0);
+          gload8_x<TX, CENTRED>(xr + j, x0, p.xs);
           d0 = __ldg(reinterpret_cast<const uint4*>(dr + j));
           if (two) {
-            gload8_x<TX, CENTRED>(xr + j + 256, x1);
+            gload8_x<TX, CENTRED>(xr + j + 256, x1, p.xs);
             d1 = __ldg(reinterpret_cast<const uint4*>(dr + j + 256));
           }
           uint32_t dw[4] = {d0.x, d0.y, d0.z, d0.w}, gw[4];
@@ -529,6 +532,7 @@ __global__ void __launch_bounds__(256) elbo_recon_kernel(const ElboParams p) {
           float x0[8], d0[8], g0[8];
           Vec8<TX>::load(xr + j, x0);
           Vec8<TD>::load(dr + j, d0);
+          scale8<TX>(x0, p.xs);
           acc += recon8<INPUT>(x0, d0, g0, s_rec);
           Vec8<TD>::store(gr + j, g0);
           j += 256;
@@ -537,7 +541,7 @@ __global__ void __launch_bounds__(256) elbo_recon_kernel(const ElboParams p) {
     } else {
       for (int j = lane; j < D; j += 32) {
         float g0;
-        acc += recon1<INPUT>(to_f32<TX>(xr[j]), to_f32<TD>(dr[j]), s_rec, g0);
+        acc += recon1<INPUT>(scale1<TX>(to_f32<TX>(xr[j]), p.xs), to_f32<TD>(dr[j]), s_rec, g0);
         gr[j] = from_f32<TD>(g0);
       }
     }

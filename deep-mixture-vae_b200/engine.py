@@ -709,8 +709,12 @@ class Engine:
         """X: device tensor [rows, D] (float32 / uint8 / bfloat16).  Fills the operand matrix act['x']."""
         xdt = {torch.float32: F32, torch.uint8: U8, torch.bfloat16: BF16}[X.dtype]
         _abi.check(self.lib.dmvae_stage_input(self.ctx, X.data_ptr(), xdt, X.stride(0), self.act["x"].data_ptr(), self.dt,
-                                              self.act["x"].stride(0), rows, self.D, self._stream()))
+                                              self.act["x"].stride(0), rows, self.D, self.x_scale, self._stream()))
         return X, xdt
+
+    # value of one unit of a uint8 input: 1 for binarised data stored as 0/1, 1/255 for 8-bit intensities (Dataset sets it
+    # from its storage format); float inputs are values already and ignore it
+    x_scale = 1.0
 
     # ------------------------------------------------------------------------------------------
     # forward
@@ -927,6 +931,7 @@ class Engine:
         ea.d_mean_kl, ea.d_log_var_kl, ea.ld_dkl = self.dmean_kl.data_ptr(), self.dlogvar_kl.data_ptr(), self.L
         ea.d_Z_gamma, ea.ld_dzg = self.dz_gamma.data_ptr(), self.L
         ea.w_scratch, ea.f_scratch = self.w_scratch.data_ptr(), self.f_scratch.data_ptr()
+        ea.x_scale = self.x_scale
         return ea
 
     def elbo(self, X, xdt, rows, kl_ratio=1.0, inv_global_batch=None, recon_scale=1.0, prior_grads=True, klr_dev=None,
@@ -1221,7 +1226,7 @@ class Engine:
             self.step_count += 1
 
     def _moe_step_graph(self, X, Y, rows, opt, kl_ratio):
-        key = ("moe", X.data_ptr(), X.dtype, Y.data_ptr(), rows, id(opt), float(kl_ratio))
+        key = ("moe", X.data_ptr(), X.dtype, Y.data_ptr(), rows, id(opt), float(kl_ratio), float(self.x_scale))
         ent = self._graphs.get(key)
         if ent is None:
             self.moe_step(X, Y, rows, opt, kl_ratio=kl_ratio, graph=False)       # eager: warms descriptor caches
@@ -1351,7 +1356,7 @@ class Engine:
 
     def _train_step_graph(self, X, rows, opt, kl_ratio, mode, recon_scale):
         key = (X.data_ptr(), X.dtype, X.stride(0), rows, mode, id(opt), float(recon_scale),
-               float(kl_ratio) if mode != "all" else None)
+               float(kl_ratio) if mode != "all" else None, float(self.x_scale))
         ent = self._graphs.get(key)
         if ent is None:
             # first use of this signature: one eager step (also warms the TMA-descriptor cache and the kernels'
@@ -1414,7 +1419,8 @@ class Engine:
         self._graph_replay_launches += n_nodes
 
     def run_epoch(self, host: torch.Tensor, batch_size: int, opt: AdamState, kl_ratio: float = 1.0, mode: str = "all",
-                  max_steps: Optional[int] = None, perm: Optional[np.ndarray] = None, while_busy=None) -> float:
+                  max_steps: Optional[int] = None, perm: Optional[np.ndarray] = None, while_busy=None,
+                  x_scale: float = 1.0) -> float:
         """One pass over a (pinned) host array [N, D].  Per step, on a copy stream and double-buffered so that it overlaps
         the previous step: the batch's rows cross the bus into a staging buffer - a plain asynchronous copy of a
         contiguous slice, or with ``perm`` (the epoch's shuffle, includes/utils.py:450-454) a gather kernel that reads the
@@ -1422,6 +1428,7 @@ class Engine:
         asynchronous read of its loss.  One synchronisation at the end.  Returns the mean batch loss
         (base_models.py:130)."""
         N = host.shape[0]
+        self.x_scale = float(x_scale)
         nb = (N + batch_size - 1) // batch_size
         if max_steps is not None:
             nb = min(nb, max_steps)
@@ -1483,10 +1490,12 @@ class Engine:
         return float(self._loss_host[:nb, col].sum()) / nb
 
     def run_epoch_moe(self, host_x: torch.Tensor, host_y: torch.Tensor, batch_size: int, opt: AdamState, kl_ratio: float = 1.0,
-                      perm: Optional[np.ndarray] = None, max_steps: Optional[int] = None, while_busy=None) -> np.ndarray:
+                      perm: Optional[np.ndarray] = None, max_steps: Optional[int] = None, while_busy=None,
+                      x_scale: float = 1.0) -> np.ndarray:
         """One pass of the MoE training step (models.py:194-221) over pinned host arrays X [N, D] / Y [N, O], batches staged
         like run_epoch.  Returns per-step [supervised loss sum, error sum, recon, KL_c, KL_z, VAE loss] as a host array."""
         N = host_x.shape[0]
+        self.x_scale = float(x_scale)
         O = host_y.shape[1]
         nb = (N + batch_size - 1) // batch_size
         if max_steps is not None:

@@ -153,11 +153,27 @@ def _pinned(a: np.ndarray, dtype) -> torch.Tensor:
     return t
 
 
-def _storage_dtype(data: np.ndarray):
-    """uint8 when the data is exactly {0,1}-valued (lossless; 4x less host->device traffic), else float32."""
+def _storage_format(data: np.ndarray):
+    """(dtype, scale): uint8 with scale 1 when the data is exactly {0,1}-valued, uint8 with scale 1/255 when it is
+    8-bit intensities k/255 (the CIFAR pixels of includes/utils.py:204-210) - both lossless up to float32 rounding and
+    4x less host->device traffic and device re-reads - else float32 with scale 1."""
     if data.size and np.all((data == 0) | (data == 1)):
-        return np.uint8
-    return np.float32
+        return np.uint8, 1.0
+    if data.size and data.min() >= 0 and data.max() <= 1:
+        k = np.rint(data * 255.0)
+        if np.all(np.abs(data * 255.0 - k) < 1e-3):
+            return np.uint8, 1.0 / 255.0
+    return np.float32, 1.0
+
+
+def _storage_dtype(data: np.ndarray):
+    return _storage_format(data)[0]
+
+
+def _to_storage(data: np.ndarray, dtype, scale) -> np.ndarray:
+    if dtype == np.uint8 and scale != 1.0:
+        return np.rint(data * 255.0).astype(np.uint8)
+    return data
 
 
 class Dataset:
@@ -198,9 +214,11 @@ class Dataset:
     def host_tensor(self) -> torch.Tensor:
         """Pinned host copy in storage dtype (uint8 for binarised data), rows in their ORIGINAL order; built once."""
         if self._host is None:
-            dt = _storage_dtype(self.data) if self._compact else np.float32
-            self._host = _pinned(self.data, dt)
+            dt, self.host_scale = _storage_format(self.data) if self._compact else (np.float32, 1.0)
+            self._host = _pinned(_to_storage(self.data, dt, self.host_scale), dt)
         return self._host
+
+    host_scale = 1.0        # value of one unit of host_tensor() (1/255 for 8-bit intensities stored as uint8)
 
     def begin_epoch(self):
         """New epoch order, drawn like get_batches does at the start of every epoch (utils.py:450-454)."""
@@ -241,8 +259,11 @@ class MEDataset:
         """Pinned host copies (data in storage dtype, labels float32), rows in their original order; built once."""
         if self._host is None:
             lab = self.labels.reshape(self.len, -1)
-            self._host = (_pinned(self.data, _storage_dtype(self.data)), _pinned(lab, np.float32))
+            dt, self.host_scale = _storage_format(self.data)
+            self._host = (_pinned(_to_storage(self.data, dt, self.host_scale), dt), _pinned(lab, np.float32))
         return self._host
+
+    host_scale = 1.0
 
     def begin_epoch(self):
         if self.shuffle:

@@ -101,9 +101,12 @@ int dmvae_linear_wgrad(dmvae_ctx* ctx, int dtype, const void* X, int64_t ldx, co
                        int accumulate, int split_k, void* stream);
 
 /* ---- input staging ------------------------------------------------------------------------- */
-/* X (f32 / u8 / bf16, [rows, D], ldx) -> A0 (out_dtype, [rows, ld_out]) with the ones column at D. */
+/* X (f32 / u8 / bf16, [rows, D], ldx) -> A0 (out_dtype, [rows, ld_out]) with the ones column at D.
+ * x_scale: value of one unit of a uint8 input (1 for binarised data stored as 0/1, 1/255 for 8-bit intensities such as
+ * the CIFAR pixels of includes/utils.py:204-210, which then travel and are re-read at 1 byte per element); ignored for
+ * the other dtypes; 0 means 1. */
 int dmvae_stage_input(dmvae_ctx* ctx, const void* X, int x_dtype, int64_t ldx, void* A0, int out_dtype,
-                      int64_t ld_out, int rows, int D, void* stream);
+                      int64_t ld_out, int rows, int D, float x_scale, void* stream);
 
 /* Shuffled minibatch: dst[i, :] = src[idx[i], :], row_bytes per row (replaces the per-row Python append of
  * Dataset.get_batches, includes/utils.py:449-463).  idx is a DEVICE int32 array; src may be a PINNED HOST buffer
@@ -202,6 +205,7 @@ typedef struct dmvae_elbo_args {
    * supervised loss gated by gamma (models.py:74).  Added through gamma's softmax Jacobian to d_s, so it reaches Z,
    * mean / log_var and the prior tables together with the ELBO's own gradient. */
   const float* d_gate_extra; int64_t ld_dge;
+  float x_scale;           /* uint8 targets: value of one unit (see dmvae_stage_input); 0 means 1 */
 } dmvae_elbo_args;
 int dmvae_elbo_fwd_bwd(dmvae_ctx* ctx, const dmvae_elbo_args* a, void* stream);
 

@@ -76,15 +76,22 @@ def make_engine(cfg, rows, device=None, gemm_dtype="bf16", seed=0):
     if cfg["model"] == "dmoe":
         moe = dict(n_experts=cfg["n_experts"], output_dim=cfg["output_dim"], featLearn=False, lossVAE=False,
                    classification=True, scope="moe/moe/moe")
-    return Engine(model=model, input_type="binary", input_dim=cfg["D"], latent_dim=cfg["L"], n_classes=cfg["K"],
-                  trunk=cfg["trunk"], head=cfg["head"], decoder=cfg["decoder"], name=model, gemm_dtype=gemm_dtype,
-                  max_rows=rows, device=device, seed=seed, moe=moe)
+    eng = Engine(model=model, input_type="binary", input_dim=cfg["D"], latent_dim=cfg["L"], n_classes=cfg["K"],
+                 trunk=cfg["trunk"], head=cfg["head"], decoder=cfg["decoder"], name=model, gemm_dtype=gemm_dtype,
+                 max_rows=rows, device=device, seed=seed, moe=moe)
+    eng.x_scale = x_scale(cfg)
+    return eng
 
 
 def synth_inputs(cfg, n_rows, seed=1):
-    """SURVEY 8(d) synthetic inputs: binarised 1{u < 0.1307} as uint8, or randint(0,256)/255 as float32 (soft targets)."""
+    """SURVEY 8(d) synthetic inputs in STORAGE form (uint8): binarised 1{u < 0.1307} as 0/1, or 8-bit intensities
+    randint(0,256) whose value is byte * x_scale(cfg) = byte / 255 (soft targets, includes/utils.py:204-210)."""
     import numpy as np
     rng = np.random.RandomState(seed)
     if cfg["binarised"]:
         return (rng.uniform(size=(n_rows, cfg["D"])) < 0.1307).astype(np.uint8)
-    return (rng.randint(0, 256, size=(n_rows, cfg["D"])) / 255.0).astype(np.float32)
+    return rng.randint(0, 256, size=(n_rows, cfg["D"])).astype(np.uint8)
+
+
+def x_scale(cfg) -> float:
+    return 1.0 if cfg["binarised"] else 1.0 / 255.0

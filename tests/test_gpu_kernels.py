@@ -149,7 +149,7 @@ def test_gemm_bf16_epilogue(lib, ctx):
 # fused ELBO
 # ---------------------------------------------------------------------------------------------
 def _run_elbo(lib, ctx, mode, input_type, X, dec, mean, lv, logits, eps, zeta, tau, m, plv, r, s, x_dtype=0, dec_dtype=0,
-              recon_scale=1.0):
+              recon_scale=1.0, x_scale=0.0):
     from dmvae_b200 import _abi
     B, D = X.shape
     L, K = mean.shape[1], m.shape[0]
@@ -185,6 +185,7 @@ def _run_elbo(lib, ctx, mode, input_type, X, dec, mean, lv, logits, eps, zeta, t
     pm, pl = dev(m), dev(plv)
     ea.prior_means, ea.prior_log_vars = pm.data_ptr(), pl.data_ptr()
     ea.kl_ratio, ea.inv_global_batch, ea.recon_scale = r, s, recon_scale
+    ea.x_scale = x_scale
     out["per_sample"] = torch.zeros(B, 4, device="cuda")
     out["qc"] = torch.zeros(B, K, device="cuda")
     out["argmax"] = torch.zeros(B, dtype=torch.int32, device="cuda")
@@ -271,6 +272,24 @@ def test_elbo_u8_and_bf16_variants(lib, ctx, B):
     assert np.all(np.abs(got["per_sample"] - ref_ps) <= 1e-3 * np.abs(ref_ps) + 2e-5)
     assert relerr(got["d_decoded"][:, :D], cb["d_decoded"]) < 1e-2          # bf16 store
     assert relerr(got["d_logits"][:, :K], cb["d_logits"]) < 1e-2
+
+
+@pytest.mark.parametrize("B,D,L,K", [(100, 784, 10, 10), (70, 3072, 40, 24)])
+@pytest.mark.parametrize("dec_dtype", [0, 1])
+def test_elbo_uint8_intensities_with_scale(lib, ctx, B, D, L, K, dec_dtype):
+    """8-bit targets x = byte / 255 (the CIFAR-shaped soft targets of includes/utils.py:204-210) read as uint8 with
+    x_scale = 1/255: row-tile kernel (K*L <= 512) and the MMA + streaming kernels, fp32 and bf16 decoder logits."""
+    X, dec, mean, lv, logits, eps, m, plv = _elbo_inputs(B, D, L, K, 7, True)
+    Xb = np.random.RandomState(8).randint(0, 256, size=(B, D)).astype(np.float32)         # byte values
+    dec_ref = _bf(dec) if dec_dtype == 1 else dec
+    c = cf.elbo_dmvae(*[a.astype(np.float64) for a in (Xb / 255.0, dec_ref, mean, lv, logits, m, plv)], r=0.9, s=1.0 / B)
+    got = _run_elbo(lib, ctx, 0, 0, Xb, dec, mean, lv, logits, None, None, 1.0, m, plv, 0.9, 1.0 / B, x_dtype=2,
+                    dec_dtype=dec_dtype, x_scale=1.0 / 255.0)
+    ref_ps = np.stack([c["R"], c["C"], c["Zk"], c["elbo"]], 1)
+    tol = 1e-4 if dec_dtype == 0 else 1e-3
+    assert np.all(np.abs(got["per_sample"] - ref_ps) <= tol * np.abs(ref_ps) + 2e-5)
+    assert relerr(got["d_decoded"][:, :D], c["d_decoded"]) < (1e-4 if dec_dtype == 0 else 1e-2)
+    assert np.array_equal(got["argmax"], c["argmax"])
 
 
 def test_elbo_sampled(lib, ctx):
@@ -482,7 +501,7 @@ def test_stage_input_and_argmax(lib, ctx):
     X = (rs.uniform(size=(B, D)) < .13).astype(np.uint8)
     Xd = torch.tensor(X, device="cuda")
     A = torch.full((B, 832), 3.0, dtype=torch.bfloat16, device="cuda")
-    _abi.check(lib.dmvae_stage_input(ctx, Xd.data_ptr(), 2, D, A.data_ptr(), 1, 832, B, D, stream()))
+    _abi.check(lib.dmvae_stage_input(ctx, Xd.data_ptr(), 2, D, A.data_ptr(), 1, 832, B, D, 1.0, stream()))
     a = A.float().cpu().numpy()
     assert np.array_equal(a[:, :D], X) and np.all(a[:, D] == 1) and np.all(a[:, D + 1:] == 0)
     sc = rs.randn(1000, 10).astype(np.float32); sc[5, 3] = sc[5, 7] = 99.0

@@ -194,3 +194,31 @@ def test_oracle_reproduces_golden_fixtures(fname, model):
     import torch
     out32, _ = rg.loss_and_grads(cfg, V, z["X"], z["eps"], kl_ratio=float(z["kl_ratio"]), dtype=torch.float32)
     assert abs(out32["loss"] - z["out:loss"]) < 1e-5 * abs(z["out:loss"])
+
+
+def test_dataset_storage_format_and_epoch_order():
+    """Dataset keeps its rows in place and draws a permutation per epoch (utils.py:450-454); binarised data is stored as
+    uint8 0/1, 8-bit intensities k/255 as uint8 with scale 1/255, anything else as float32."""
+    from dmvae_b200.includes.utils import Dataset, MEDataset, _storage_format
+    rs = np.random.RandomState(0)
+    xb = (rs.uniform(size=(50, 12)) < 0.3).astype(np.float32)
+    xi = (rs.randint(0, 256, size=(50, 12)) / 255.0).astype(np.float32)
+    xr = rs.uniform(size=(50, 12)).astype(np.float32)
+    assert _storage_format(xb) == (np.uint8, 1.0)
+    assert _storage_format(xi) == (np.uint8, 1.0 / 255.0)
+    assert _storage_format(xr) == (np.float32, 1.0)
+    d = Dataset((xi, np.arange(50)), batch_size=16)
+    h = d.host_tensor()
+    assert h.dtype.__str__() == "torch.uint8" and d.host_scale == 1.0 / 255.0
+    assert np.array_equal(h.numpy(), np.rint(xi * 255).astype(np.uint8))
+    np.random.seed(1)
+    batches = list(d.get_batches())
+    assert sorted(d.perm.tolist()) == list(range(50)) and len(batches) == 4 and len(batches[-1]) == 2
+    assert np.array_equal(np.concatenate(batches), xi[d.perm]) and np.array_equal(d.epoch_classes(), d.perm)
+    d.prefetch_epoch()
+    nxt = d._next_perm.copy()
+    d.begin_epoch()
+    assert np.array_equal(d.perm, nxt) and d._next_perm is None
+    me = MEDataset((xb, np.arange(50), np.eye(5)[np.arange(50) % 5]), batch_size=20)
+    got = list(me.get_batches())
+    assert np.array_equal(np.concatenate([g[2] for g in got]), me.perm) and got[0][1].shape == (20, 5)
