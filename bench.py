@@ -95,6 +95,15 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def ncu_traffic(config, key):
+    """DRAM bytes per step of a kernel family from this round's committed ncu capture (profiles/r02_traffic.json), or None."""
+    tp = os.path.join(ROOT, "profiles", "r02_traffic.json")
+    if not os.path.exists(tp):
+        return None
+    with open(tp) as f:
+        return json.load(f).get("cfg%d" % config, {}).get(key)
+
+
 def dbg(msg):
     if os.environ.get("DMVAE_BENCH_DEBUG"):
         print("[bench %s] %s" % (os.environ.get("RANK", "0"), msg), file=sys.stderr, flush=True)
@@ -364,7 +373,7 @@ def run_ours(args):
         "clocks": clk,
         "roofline": {"kernel": "tcgen05 GEMM family: gemm_tc2_kernel / gemm_chain_kernel / gemm_tc_kernel (%d launches per step)" % len(gemm_rows),
                      "bound": "tensor", "achieved": tf_launch, "peak": pk["tf_sust"], "unit": "TFLOP/s",
-                     "frac": tf_launch / pk["tf_sust"], "traffic": None, "peak_source": pk["src"],
+                     "frac": tf_launch / pk["tf_sust"], "traffic": ncu_traffic(args.config, "gemm"), "peak_source": pk["src"],
                      "flop_per_step": flop, "us_per_step": gemm_us, "step_frac": tf_step / pk["tf_sust"],
                      "timing": "every GEMM launch of one step re-issued with the engine's own arguments, 20x back to back in a "
                                "CUDA graph, CUDA events on the launching stream; step_frac = the same FLOPs over the whole timed step"},
@@ -372,11 +381,7 @@ def run_ours(args):
     }
     if elbo_us is not None:
         eb = CFG.elbo_bytes_per_sample(cfg, 1, logit_bytes) * B
-        traffic = None
-        tp = os.path.join(ROOT, "profiles", "r02_elbo_traffic.json")
-        if os.path.exists(tp):
-            with open(tp) as f:
-                traffic = json.load(f).get("cfg%d" % args.config)
+        traffic = ncu_traffic(args.config, "elbo")
         out["roofline_elbo"] = {"kernel": "fused ELBO fwd+bwd (elbo_rowtile_kernel, or elbo_latent_mma_kernel + elbo_recon_kernel)",
                                 "bound": "hbm", "achieved": eb / (elbo_us * 1e-6) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
                                 "frac": eb / (elbo_us * 1e-6) / 1e9 / pk["hbm"], "traffic": traffic, "bytes_per_launch": eb,
