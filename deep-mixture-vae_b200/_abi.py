@@ -25,10 +25,15 @@ class DmvaeError(RuntimeError):
     pass
 
 
+class ReconFuse(C.Structure):
+    _fields_ = [("X", c_void_p), ("x_dtype", c_int32), ("ldx", c_int64), ("x_scale", c_float), ("input_type", c_int32),
+                ("scale", c_float), ("D", c_int32), ("r_part", c_void_p), ("r_parts", c_int32)]
+
+
 class GemmEpilogue(C.Structure):
     _fields_ = [("out_dtype", c_int32), ("act", c_int32), ("n_valid", c_int32), ("n_block", c_int32),
                 ("pad_one", c_float), ("relu_mask", c_void_p), ("ld_mask", c_int64), ("bias", c_void_p),
-                ("accumulate", c_int32), ("split_k", c_int32)]
+                ("accumulate", c_int32), ("split_k", c_int32), ("recon", C.POINTER(ReconFuse))]
 
 
 class ChainGemm(C.Structure):
@@ -67,7 +72,8 @@ class ElboArgs(C.Structure):
                 ("d_logits", c_void_p), ("dlogits_dtype", c_int32), ("ld_dlogits", c_int64), ("dlogits_cols", c_int32),
                 ("d_Z_gamma", c_void_p), ("ld_dzg", c_int64),
                 ("w_scratch", c_void_p), ("f_scratch", c_void_p),
-                ("d_gate_extra", c_void_p), ("ld_dge", c_int64), ("x_scale", c_float)]
+                ("d_gate_extra", c_void_p), ("ld_dge", c_int64), ("x_scale", c_float),
+                ("r_part", c_void_p), ("r_parts", c_int32)]
 
 
 class MoeArgs(C.Structure):
@@ -107,6 +113,8 @@ SIGNATURES = {
     "dmvae_elbo_fwd_bwd": (c_int, [c_void_p, C.POINTER(ElboArgs), c_void_p]),
     "dmvae_elbo_reduce_workspace": (c_int64, [c_int, c_int, c_int]),
     "dmvae_elbo_reduce": (c_int, [c_void_p, C.POINTER(ElboArgs), c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    "dmvae_elbo_reduce_stage": (c_int, [c_void_p, C.POINTER(ElboArgs), c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int,
+                                        c_void_p]),
     "dmvae_moe_fwd_bwd": (c_int, [c_void_p, C.POINTER(MoeArgs), c_void_p]),
     "dmvae_softmax_bwd_add": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int64, c_void_p, c_int, c_int64,
                                       c_int, c_int, c_void_p]),

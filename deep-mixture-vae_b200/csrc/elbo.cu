@@ -606,7 +606,7 @@ __device__ __forceinline__ void rowtile_store_q(const dmvae_elbo_args& a, const 
 // components produces both A_k (quad-reduced) and the KL-side gradients - q = softmax(logits) does not depend on A, so
 // the two passes of the formulas (SURVEY 8a') fuse.  The prior table is zero-padded to 4 LQ columns: padded (l >= L)
 // entries contribute exact zeros.  ~7 issue slots per (k, l) pair instead of ~20 for the generic two-pass loops.
-template <int LQ>
+template <int LQ, bool LO = false>
 __device__ __forceinline__ void rowtile_latent(const dmvae_elbo_args& a, float* smem, const RowTileSmem& sm, int row0,
                                                int nrows_cta, int lw, int lane, float r, float s) {
   constexpr int Ls = 4 * LQ;
@@ -748,12 +748,33 @@ __device__ __forceinline__ void rowtile_latent(const dmvae_elbo_args& a, float* 
     rowtile_store_dlogits(a, g_r, grow, h, K);
   }
   rowtile_store_q(a, smem + sm.q + lr0 * K, row0 + lr0, nrows_l * K, lane);
-  asm volatile("bar.sync 1, %0;" ::"n"(kFastThreads) : "memory");             // every slab's R_s is written
+  if (!LO) asm volatile("bar.sync 1, %0;" ::"n"(kFastThreads) : "memory");    // every slab's R_s is written
   if (valid && h == 0) {
-    const float R = R_s[rl];
+    const float R = LO ? 0.f : R_s[rl];       // latent-only launch: dmvae_elbo_reduce completes .x and .w from r_part
     reinterpret_cast<float4*>(a.per_sample)[row0 + rl] = make_float4(R, C, Zk, a.recon_scale * R + r * (C + Zk));
     a.argmax[row0 + rl] = amax;
   }
+}
+
+// The latent warps of the row-tile kernel alone (dmvae_elbo_args.r_part: the reconstruction term lives in the output
+// layer's GEMM epilogue).  64 threads and a few KB of shared memory per 16-row tile: these CTAs fit beside the resident
+// GEMM CTAs of the decoder's forward pass, which this launch overlaps.
+__global__ void __launch_bounds__(32 * kLatWarps) elbo_rowtile_latent_kernel(const ElboParams p) {
+  extern __shared__ __align__(128) float smem[];
+  const dmvae_elbo_args& a = p.a;
+  const RowTileSmem sm(a.L, a.K);
+  const int lw = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row0 = blockIdx.x * kFastRows;
+  const int nrows_cta = min(kFastRows, a.rows - row0);
+  pdl_wait();
+  pdl_launch_dependents();
+  const float r = a.kl_ratio_dev ? __ldg(a.kl_ratio_dev) : a.kl_ratio;
+  const float s = a.inv_global_batch;
+  const int lq = (a.L + 3) >> 2;
+  if (lq == 1) rowtile_latent<1, true>(a, smem, sm, row0, nrows_cta, lw, lane, r, s);
+  else if (lq == 2) rowtile_latent<2, true>(a, smem, sm, row0, nrows_cta, lw, lane, r, s);
+  else if (lq == 3) rowtile_latent<3, true>(a, smem, sm, row0, nrows_cta, lw, lane, r, s);
+  else rowtile_latent<4, true>(a, smem, sm, row0, nrows_cta, lw, lane, r, s);
 }
 
 template <typename TX, typename TD, int INPUT, bool PRECISE>
@@ -1118,6 +1139,25 @@ int launch_elbo(dmvae_ctx* ctx, const ElboParams& p, cudaStream_t st) {
   return launch_elbo_k<TX, TD, INPUT, 4>(ctx, p, st);
 }
 
+// dmvae_elbo_args.r_part: latent part only (the reconstruction term is the output-layer GEMM's, dmvae_recon_fuse)
+int launch_elbo_latent_only(dmvae_ctx* ctx, const ElboParams& p, cudaStream_t st) {
+  const dmvae_elbo_args& a = p.a;
+  static int rt_enabled = -1;
+  if (rt_enabled < 0) {
+    const char* e = getenv("DMVAE_ELBO_ROWTILE");
+    rt_enabled = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (rt_enabled && a.mode == DMVAE_MODE_DMVAE && a.L <= 16 && a.K <= 64 && a.K * a.L <= 512 && ((uintptr_t)a.d_logits & 15) == 0) {
+    const size_t smem = sizeof(float) * (size_t)RowTileSmem(a.L, a.K).total;
+    const int blocks = (a.rows + kFastRows - 1) / kFastRows;
+    dmvae_launch(elbo_rowtile_latent_kernel, dim3(blocks), dim3(32 * kLatWarps), smem, st, true, p);
+    DMVAE_LAUNCH_CHECK(ctx);
+    return DMVAE_OK;
+  }
+  DMVAE_CHECK_ARG(elbo_mma_ok(p), "elbo: latent-only launch (r_part) is not available for mode %d, L=%d, K=%d", a.mode, a.L, a.K);
+  return launch_elbo_mma_latent(ctx, p, st);
+}
+
 int check_elbo_args(const dmvae_elbo_args* a) {
   DMVAE_CHECK_ARG(a != nullptr, "elbo: args is NULL");
   DMVAE_CHECK_ARG(a->mode >= 0 && a->mode <= 2, "elbo: unknown mode %d", a->mode);
@@ -1125,10 +1165,14 @@ int check_elbo_args(const dmvae_elbo_args* a) {
                   "elbo: input_type %d not implemented (binary | real)", a->input_type);   // base_models.py:84-85
   DMVAE_CHECK_ARG(a->rows >= 0 && a->D > 0 && a->L > 0 && a->K > 0, "elbo: bad sizes rows=%d D=%d L=%d K=%d", a->rows, a->D, a->L, a->K);
   DMVAE_CHECK_ARG(a->K <= kMaxK, "elbo: K=%d exceeds the supported maximum %d", a->K, kMaxK);
-  DMVAE_CHECK_ARG(a->X && a->decoded && a->mean && a->log_var && a->prior_means && a->prior_log_vars, "elbo: NULL input");
-  DMVAE_CHECK_ARG(a->per_sample && a->qc && a->argmax && a->d_decoded && a->d_mean_kl && a->d_log_var_kl, "elbo: NULL output");
+  const bool latent_only = a->r_part != nullptr;
+  DMVAE_CHECK_ARG(!latent_only || a->r_parts > 0, "elbo: r_part needs r_parts > 0");
+  DMVAE_CHECK_ARG(a->mean && a->log_var && a->prior_means && a->prior_log_vars, "elbo: NULL input");
+  DMVAE_CHECK_ARG(latent_only || (a->X && a->decoded), "elbo: NULL input");
+  DMVAE_CHECK_ARG(a->per_sample && a->qc && a->argmax && a->d_mean_kl && a->d_log_var_kl && (latent_only || a->d_decoded), "elbo: NULL output");
   DMVAE_CHECK_ARG(((uintptr_t)a->per_sample & 15) == 0, "elbo: per_sample must be 16-byte aligned");
-  DMVAE_CHECK_ARG(a->ldx >= a->D && a->ld_dec >= a->D && a->ld_ddec >= a->D && a->ddec_cols <= a->ld_ddec, "elbo: leading dimensions too small");
+  DMVAE_CHECK_ARG(latent_only || (a->ldx >= a->D && a->ld_dec >= a->D && a->ld_ddec >= a->D && a->ddec_cols <= a->ld_ddec),
+                  "elbo: leading dimensions too small");
   if (a->mode == DMVAE_MODE_VADE)
     DMVAE_CHECK_ARG(a->eps && a->d_Z_gamma && a->w_scratch, "elbo(VADE): eps, d_Z_gamma and w_scratch are required");
   else
@@ -1164,6 +1208,7 @@ extern "C" int dmvae_elbo_fwd_bwd(dmvae_ctx* ctx, const dmvae_elbo_args* a, void
   DMVAE_CHECK_ARG(elbo_mma_ok(p) || elbo_smem_bytes(a->L, a->K, p.Ls) <= 220 * 1024,
                   "elbo: K*L = %d too large for the shared prior tables", a->K * a->L);
   cudaStream_t st = (cudaStream_t)stream;
+  if (a->r_part) return launch_elbo_latent_only(ctx, p, st);
 #define GO(TX, TD)                                                                            \
   return a->input_type == DMVAE_INPUT_BINARY ? launch_elbo<TX, TD, DMVAE_INPUT_BINARY>(ctx, p, st) \
                                              : launch_elbo<TX, TD, DMVAE_INPUT_REAL>(ctx, p, st)
@@ -1198,7 +1243,7 @@ inline int reduce_chunk(int L, int K) {
 }
 
 __global__ void __launch_bounds__(kRedThreads) elbo_reduce_partial_kernel(const dmvae_elbo_args a, int chunk, int G,
-                                                                          float* __restrict__ ws) {
+                                                                          float* __restrict__ ws, int do_loss) {
   extern __shared__ float sm[];
   pdl_wait();
   pdl_launch_dependents();
@@ -1243,11 +1288,11 @@ __global__ void __launch_bounds__(kRedThreads) elbo_reduce_partial_kernel(const 
     for (int b = 0; b < nb; ++b) acc += w_sm[b * K + k] * f_sm[b * nF + f];
     out[o] = acc;
   }
-  if (set == 0 && threadIdx.x < 32) {
+  if (do_loss && set == 0 && threadIdx.x < 32) {
     // loss partials: per_sample[b] = (R, C, Zk, total)
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int b = threadIdx.x; b < nb; b += 32) {
-      float4 v = reinterpret_cast<const float4*>(a.per_sample)[b0 + b];
+      float4 v = finish_per_sample(a, b0 + b);
       acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
     }
     acc.x = warp_sum(acc.x); acc.y = warp_sum(acc.y); acc.z = warp_sum(acc.z); acc.w = warp_sum(acc.w);
@@ -1256,6 +1301,30 @@ __global__ void __launch_bounds__(kRedThreads) elbo_reduce_partial_kernel(const 
       float* lp = ws + (size_t)nsets * G * (size_t)(K * nF) + (size_t)g * 4;
       lp[0] = acc.x; lp[1] = acc.y; lp[2] = acc.z; lp[3] = acc.w;
     }
+  }
+}
+
+// Stage 2 of the split reduction (fused reconstruction term): complete per_sample from the r_part slots and write the loss
+// partials of `chunk` rows per block - no shared memory, so these blocks fit beside resident GEMM CTAs.
+__global__ void __launch_bounds__(64) elbo_finish_rows_kernel(const dmvae_elbo_args a, int chunk, int G, float* __restrict__ ws) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int L = a.L, K = a.K, nF = 2 * L + 1;
+  const int g = blockIdx.x, b0 = g * chunk;
+  const int nb = min(chunk, a.rows - b0);
+  __shared__ float4 wsum[2];
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int b = threadIdx.x; b < nb; b += 64) {
+    const float4 v = finish_per_sample(a, b0 + b);
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  acc.x = warp_sum(acc.x); acc.y = warp_sum(acc.y); acc.z = warp_sum(acc.z); acc.w = warp_sum(acc.w);
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int nsets = (a.mode == DMVAE_MODE_VADE) ? 2 : 1;
+    float* lp = ws + (size_t)nsets * G * (size_t)(K * nF) + (size_t)g * 4;
+    lp[0] = wsum[0].x + wsum[1].x; lp[1] = wsum[0].y + wsum[1].y; lp[2] = wsum[0].z + wsum[1].z; lp[3] = wsum[0].w + wsum[1].w;
   }
 }
 
@@ -1340,7 +1409,13 @@ extern "C" int64_t dmvae_elbo_reduce_workspace(int rows, int L, int K) {
 
 extern "C" int dmvae_elbo_reduce(dmvae_ctx* ctx, const dmvae_elbo_args* a, float* d_prior_means, float* d_prior_log_vars,
                                  int accumulate, float* loss_out, float* workspace, void* stream) {
+  return dmvae_elbo_reduce_stage(ctx, a, d_prior_means, d_prior_log_vars, accumulate, loss_out, workspace, 0, stream);
+}
+
+extern "C" int dmvae_elbo_reduce_stage(dmvae_ctx* ctx, const dmvae_elbo_args* a, float* d_prior_means, float* d_prior_log_vars,
+                                       int accumulate, float* loss_out, float* workspace, int stage, void* stream) {
   DMVAE_CHECK_ARG(ctx != nullptr, "elbo_reduce: ctx is NULL");
+  DMVAE_CHECK_ARG(stage >= 0 && stage <= 2, "elbo_reduce: stage must be 0 (all), 1 (table partials) or 2 (rows + final sums)");
   int rc = check_elbo_args(a);
   if (rc) return rc;
   DMVAE_CHECK_ARG(workspace != nullptr, "elbo_reduce: workspace is NULL");
@@ -1348,18 +1423,24 @@ extern "C" int dmvae_elbo_reduce(dmvae_ctx* ctx, const dmvae_elbo_args* a, float
   if (a->rows == 0) return DMVAE_OK;
   const int nsets = (a->mode == DMVAE_MODE_VADE) ? 2 : 1;
   cudaStream_t st = (cudaStream_t)stream;
-  int G;
-  if (elbo_reduce_mma_ok(*a)) {
-    G = (a->rows + kRedChunkM - 1) / kRedChunkM;
-    rc = launch_elbo_reduce_mma(ctx, *a, G, nsets, workspace, st);
-    if (rc) return rc;
+  const bool mma = elbo_reduce_mma_ok(*a);
+  const int chunk = mma ? kRedChunkM : reduce_chunk(a->L, a->K);
+  const int G = (a->rows + chunk - 1) / chunk;
+  const int do_loss = stage == 0 ? 1 : 0;
+  if (stage <= 1) {
+    if (mma) {
+      rc = launch_elbo_reduce_mma(ctx, *a, G, nsets, workspace, do_loss, st);
+      if (rc) return rc;
+    } else {
+      const size_t smem = sizeof(float) * (size_t)chunk * (size_t)(a->K + 2 * a->L + 1);
+      if (smem > 48 * 1024)
+        DMVAE_CUDA(cudaFuncSetAttribute(elbo_reduce_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      dmvae_launch(elbo_reduce_partial_kernel, dim3(G, nsets), dim3(kRedThreads), smem, st, true, *a, chunk, G, workspace, do_loss);
+      DMVAE_LAUNCH_CHECK(ctx);
+    }
+    if (stage == 1) return DMVAE_OK;
   } else {
-    const int chunk = reduce_chunk(a->L, a->K);
-    G = (a->rows + chunk - 1) / chunk;
-    const size_t smem = sizeof(float) * (size_t)chunk * (size_t)(a->K + 2 * a->L + 1);
-    if (smem > 48 * 1024)
-      DMVAE_CUDA(cudaFuncSetAttribute(elbo_reduce_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dmvae_launch(elbo_reduce_partial_kernel, dim3(G, nsets), dim3(kRedThreads), smem, st, true, *a, chunk, G, workspace);
+    dmvae_launch(elbo_finish_rows_kernel, dim3(G), dim3(64), 0, st, true, *a, chunk, G, workspace);
     DMVAE_LAUNCH_CHECK(ctx);
   }
   const int fin_blocks = max(1, (a->K * a->L + 31) / 32);

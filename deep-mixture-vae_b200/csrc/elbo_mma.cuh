@@ -600,16 +600,19 @@ int launch_elbo_latent_kt(dmvae_ctx* ctx, const ElboParams& p, cudaStream_t st) 
   return DMVAE_OK;
 }
 
+inline int launch_elbo_mma_latent(dmvae_ctx* ctx, const ElboParams& p, cudaStream_t st) {
+  const int kt = (p.a.K + 7) / 8;
+  if (kt <= 2) return launch_elbo_latent_kt<2>(ctx, p, st);
+  if (kt <= 4) return launch_elbo_latent_kt<4>(ctx, p, st);
+  if (kt <= 7) return launch_elbo_latent_kt<7>(ctx, p, st);
+  if (kt <= 10) return launch_elbo_latent_kt<10>(ctx, p, st);
+  if (kt <= 13) return launch_elbo_latent_kt<13>(ctx, p, st);
+  return launch_elbo_latent_kt<16>(ctx, p, st);
+}
+
 template <typename TX, typename TD, int INPUT>
 int launch_elbo_mma(dmvae_ctx* ctx, const ElboParams& p, cudaStream_t st) {
-  const int kt = (p.a.K + 7) / 8;
-  int rc;
-  if (kt <= 2) rc = launch_elbo_latent_kt<2>(ctx, p, st);
-  else if (kt <= 4) rc = launch_elbo_latent_kt<4>(ctx, p, st);
-  else if (kt <= 7) rc = launch_elbo_latent_kt<7>(ctx, p, st);
-  else if (kt <= 10) rc = launch_elbo_latent_kt<10>(ctx, p, st);
-  else if (kt <= 13) rc = launch_elbo_latent_kt<13>(ctx, p, st);
-  else rc = launch_elbo_latent_kt<16>(ctx, p, st);
+  int rc = launch_elbo_mma_latent(ctx, p, st);
   if (rc) return rc;
   const int blocks = std::max(1, std::min(ctx->sm_count * 8, (p.a.rows + 7) / 8));
   dmvae_launch(elbo_recon_kernel<TX, TD, INPUT>, dim3(blocks), dim3(256), 0, st, true, p);
@@ -624,12 +627,33 @@ int launch_elbo_mma(dmvae_ctx* ctx, const ElboParams& p, cudaStream_t st) {
 // 16-cluster block w % MT and every (8 / MT)-th 8-feature block; the chunk partials are summed in a fixed order by
 // elbo_reduce_final_kernel (deterministic).  Same workspace layout as the scalar kernel it replaces.
 // ---------------------------------------------------------------------------------------------------------------
+// Fused-reconstruction mode (dmvae_elbo_args.r_part): the output-layer GEMM left per-column-range sums of the reconstruction
+// term; the first reduce stage completes per_sample = (R, C, Zk, recon_scale R + r (C + Zk)) - one thread per row, slots
+// added in index order (deterministic).
+__device__ __forceinline__ float4 finish_per_sample(const dmvae_elbo_args& a, int64_t row) {
+  float4 v = reinterpret_cast<const float4*>(a.per_sample)[row];
+  if (a.r_part) {
+    const float r = a.kl_ratio_dev ? __ldg(a.kl_ratio_dev) : a.kl_ratio;
+    const float* rp = a.r_part + row * a.r_parts;
+    float R = 0.f;
+    for (int j = 0; j < a.r_parts; ++j) R += rp[j];
+    v.x = R;
+    v.w = a.recon_scale * R + r * (v.y + v.z);
+    reinterpret_cast<float4*>(a.per_sample)[row] = v;
+  }
+  return v;
+}
+
 constexpr int kRedChunkM = 64;
-__host__ __device__ inline int red_pad8(int n) { return ((n + 23) / 32) * 32 + 8; }        // >= n (n % 8 == 0), == 8 (mod 32)
+// row pitch of the staged operands: >= n (n % 8 == 0) and == 8 (mod 16), i.e. == +-8 (mod 32): the MMA fragment loads
+// (address t * pitch + g, t < 4, g < 8) touch 32 distinct banks either way.  The smaller pitch keeps the small-mixture
+// launch under 16 KB of shared memory, which is what fits beside a resident GEMM CTA (this kernel runs on the side stream).
+__host__ __device__ inline int red_pad8(int n) { return ((n + 7) / 16) * 16 + 8; }
 
 // grid (row chunks, sets, column groups): a CTA computes U[set][:, its 8-feature blocks] of its 64 rows
 template <int NTW>
-__global__ void __launch_bounds__(256) elbo_reduce_mma_partial_kernel(const dmvae_elbo_args a, int G, int NTC, float* __restrict__ ws) {
+__global__ void __launch_bounds__(256) elbo_reduce_mma_partial_kernel(const dmvae_elbo_args a, int G, int NTC, float* __restrict__ ws,
+                                                                      int do_loss) {
   extern __shared__ float sm[];
   const int L = a.L, K = a.K, nF = 2 * L + 1;
   const int MT = (K + 15) >> 4, NT8 = (nF + 7) >> 3;
@@ -732,11 +756,11 @@ __global__ void __launch_bounds__(256) elbo_reduce_mma_partial_kernel(const dmva
       }
     }
   }
-  if (set == 0 && cg == 0 && warp == 7) {
+  if (do_loss && set == 0 && cg == 0 && warp == 7) {
     // loss partials: per_sample[b] = (R, C, Zk, total)
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int b = lane; b < nb; b += 32) {
-      const float4 v = reinterpret_cast<const float4*>(a.per_sample)[b0 + b];
+      const float4 v = finish_per_sample(a, b0 + b);
       acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
     }
     acc.x = warp_sum(acc.x); acc.y = warp_sum(acc.y); acc.z = warp_sum(acc.z); acc.w = warp_sum(acc.w);
@@ -757,7 +781,7 @@ inline bool elbo_reduce_mma_ok(const dmvae_elbo_args& a) {
   return enabled && a.K <= 128 && a.L <= 128;
 }
 
-inline int launch_elbo_reduce_mma(dmvae_ctx* ctx, const dmvae_elbo_args& a, int G, int nsets, float* ws, cudaStream_t st) {
+inline int launch_elbo_reduce_mma(dmvae_ctx* ctx, const dmvae_elbo_args& a, int G, int nsets, float* ws, int do_loss, cudaStream_t st) {
   const int nF = 2 * a.L + 1, MT = (a.K + 15) / 16, NT8 = (nF + 7) / 8;
   const int nsplit = std::max(1, 8 / MT);
   // column groups: at most 9 feature blocks per warp (small code, ~100 registers) and enough CTAs to fill the chip
@@ -770,7 +794,7 @@ inline int launch_elbo_reduce_mma(dmvae_ctx* ctx, const dmvae_elbo_args& a, int 
   do {                                                                                                         \
     auto kern = elbo_reduce_mma_partial_kernel<N>;                                                             \
     if (smem > 48 * 1024) DMVAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    dmvae_launch(kern, dim3(G, nsets, CG), dim3(256), smem, st, true, a, G, NTC, ws);                          \
+    dmvae_launch(kern, dim3(G, nsets, CG), dim3(256), smem, st, true, a, G, NTC, ws, do_loss);                       \
   } while (0)
   if (ntw <= 3) RED_GO(3);
   else if (ntw <= 5) RED_GO(5);

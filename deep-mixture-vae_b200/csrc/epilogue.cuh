@@ -13,6 +13,12 @@ struct EpiParams {
   int64_t ld_mask;
   const float* bias;
   int accumulate;      // 0: store, 1: +=, 2: atomic += (split-K)
+  // fused reconstruction term (dmvae_recon_fuse): rx == nullptr -> off
+  const void* rx;
+  int rx_dtype, rx_input, rx_D, r_parts;
+  int64_t rx_ld;
+  float rx_scale, rx_s;
+  float* r_part;
 };
 
 static inline EpiParams make_epi_params(const dmvae_gemm_epilogue& e, int operand_dtype) {
@@ -27,6 +33,23 @@ static inline EpiParams make_epi_params(const dmvae_gemm_epilogue& e, int operan
   p.ld_mask = e.ld_mask;
   p.bias = e.bias;
   p.accumulate = e.split_k > 1 ? 2 : (e.accumulate ? 1 : 0);
+  p.rx = nullptr;
+  p.rx_dtype = p.rx_input = p.rx_D = p.r_parts = 0;
+  p.rx_ld = 0;
+  p.rx_scale = 1.f;
+  p.rx_s = 0.f;
+  p.r_part = nullptr;
+  if (e.recon) {
+    p.rx = e.recon->X;
+    p.rx_dtype = e.recon->x_dtype;
+    p.rx_ld = e.recon->ldx;
+    p.rx_scale = e.recon->x_scale == 0.f ? 1.f : e.recon->x_scale;
+    p.rx_input = e.recon->input_type;
+    p.rx_s = e.recon->scale;
+    p.rx_D = e.recon->D;
+    p.r_part = e.recon->r_part;
+    p.r_parts = e.recon->r_parts;
+  }
   return p;
 }
 

@@ -212,7 +212,7 @@ gemm_chain_kernel(const __grid_constant__ ChainParams P) {
       const ChainLayer& Ly = P.L[e];
       const uint32_t as = ui & 1u, aph = (ui >> 1) & 1u;
       const int bnh = Ly.bn >> 1;
-      epilogue_warp(tmem_base + as * CH_BN + ((uint32_t)(q * 32) << 16), half * bnh, (half + 1) * bnh,
+      epilogue_warp<false>(tmem_base + as * CH_BN + ((uint32_t)(q * 32) << 16), half * bnh, (half + 1) * bnh,
                     un.m_blk * 2 * BM + (int)rank * BM + q * 32, un.n_blk * Ly.bn, Ly.M, Ly.N, &Ly.tmC, Ly.ep, un.kb0 == 0,
                     my_stage, lane, lead_tempty0 + as * 8, (Ly.fuse && half == 0) ? &P.ra : nullptr, tfull_bar(as), aph);
       if (Ly.publish) {
@@ -281,6 +281,7 @@ extern "C" int dmvae_gemm_chain(dmvae_ctx* ctx, const dmvae_chain_gemm* g, int n
     Ly.M = e.M; Ly.N = e.N; Ly.K = e.K;
     Ly.a_mn = e.trans_a ? 1 : 0;
     Ly.b_mn = e.trans_b ? 0 : 1;
+    DMVAE_CHECK_ARG(e.epi.recon == nullptr, "gemm_chain: entry %d: the fused reconstruction epilogue is dmvae_gemm's", i);
     Ly.ep = make_epi_params(e.epi, DMVAE_BF16);
     Ly.tiles_m = (e.M + 2 * BM - 1) / (2 * BM);
     Ly.nkb = (e.K + BK - 1) / BK;

@@ -128,6 +128,7 @@ extern "C" int dmvae_gemm(dmvae_ctx* ctx, int dtype, int trans_a, int trans_b, c
   if (dtype == DMVAE_BF16) return dmvae_gemm_bf16_tc(ctx, trans_a, trans_b, A, lda, B, ldb, C, ldc, M, N, K, epi, st);
   DMVAE_CHECK_ARG(dtype == DMVAE_F32, "gemm: dtype %d unsupported", dtype);
   DMVAE_CHECK_ARG(epi->out_dtype == DMVAE_F32, "gemm(f32): output must be fp32");
+  DMVAE_CHECK_ARG(epi->recon == nullptr, "gemm(f32): the fused reconstruction epilogue exists on the bf16 tensor-core path only");
   EpiParams ep = make_epi_params(*epi, DMVAE_F32);
   const bool vecA = (lda % 4 == 0) && (((uintptr_t)A & 15) == 0);
   const bool vecB = (ldb % 4 == 0) && (((uintptr_t)B & 15) == 0);

@@ -424,6 +424,18 @@ int dmvae_gemm_bf16_tc(dmvae_ctx* ctx, int trans_a, int trans_b, const void* A, 
   if (epi->relu_mask) DMVAE_CHECK_ARG(epi->ld_mask % 8 == 0 && ((uintptr_t)epi->relu_mask & 15) == 0, "gemm(bf16): mask must be 16-byte aligned with ld % 8 == 0");
   EpiParams ep = make_epi_params(*epi, DMVAE_BF16);
   DMVAE_CHECK_ARG(epi->n_valid >= epi->n_block || epi->n_block % 32 == 0, "gemm(bf16): n_block (%d) must be a multiple of 32", epi->n_block);
+  if (epi->recon) {
+    const dmvae_recon_fuse* r = epi->recon;
+    DMVAE_CHECK_ARG(epi->out_dtype == DMVAE_BF16 && epi->act == DMVAE_ACT_NONE && epi->split_k <= 1 && !epi->accumulate && !epi->relu_mask &&
+                        epi->n_valid >= epi->n_block,
+                    "gemm(bf16): the fused reconstruction term needs a plain bf16 output layer (no activation, mask, split-K, padding columns)");
+    DMVAE_CHECK_ARG(r->X && r->r_part && r->D > 0 && r->D <= N && r->r_parts >= (N + 31) / 32 &&
+                        (r->input_type == DMVAE_INPUT_BINARY || r->input_type == DMVAE_INPUT_REAL),
+                    "gemm(bf16): recon fuse: X, r_part, 0 < D <= N, r_parts >= ceil(N / 32), binary | real");
+    DMVAE_CHECK_ARG((r->x_dtype == DMVAE_U8 && r->D % 16 == 0 && r->ldx % 16 == 0 && ((uintptr_t)r->X & 15) == 0) ||
+                        (r->x_dtype == DMVAE_F32 && r->D % 4 == 0 && r->ldx % 4 == 0 && ((uintptr_t)r->X & 15) == 0),
+                    "gemm(bf16): recon fuse: targets must be uint8 (D, ldx multiples of 16) or fp32 (multiples of 4), 16-byte aligned");
+  }
   const int split = epi->split_k;
   // op(A) [M,K]: trans_a=0 -> stored [M,K] = K-major; trans_a=1 -> stored [K,M] = MN-major
   // op(B) [K,N]: trans_b=0 -> stored [K,N] = MN-major; trans_b=1 -> stored [N,K] = K-major

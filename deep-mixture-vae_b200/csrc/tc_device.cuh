@@ -219,7 +219,7 @@ __device__ __forceinline__ void fused_reparam_row(uint32_t stage, int lane, int 
 // stage      : shared-memory address (1024-byte aligned) of this warp's private 4 KiB slab
 // arrive_bar : cluster address of the "accumulator drained" barrier (0: none); signalled right after the last
 //              TMEM read so that the MMA issuer can reuse the buffer while this warp still converts and stores
-template <bool OUT_BF16, bool RELU, bool MASK, bool FUSE = false>
+template <bool OUT_BF16, bool RELU, bool MASK, bool FUSE = false, bool RECON = false>
 __device__ __forceinline__ void epilogue_warp_cols(uint32_t taddr, int col_begin, int col_end, int m_base, int n0, int M, int N,
                                                    const CUtensorMap* tmC, const EpiParams& ep, bool first_split,
                                                    uint32_t stage, int lane, uint32_t arrive_bar,
@@ -231,8 +231,10 @@ __device__ __forceinline__ void epilogue_warp_cols(uint32_t taddr, int col_begin
   const int m = m_base + lane;
   const __nv_bfloat16* mrow = MASK ? reinterpret_cast<const __nv_bfloat16*>(ep.mask) + (int64_t)m * ep.ld_mask : nullptr;
   const bool m_ok = m < M;
+  const int part_w = col_end - col_begin;                 // RECON: width of this warp's column range = one r_part slot
   if (col_end > N - n0) col_end = N - n0;                 // N % 8 == 0
   bool arrived = false;
+  float r_row = 0.f;                                      // RECON: reconstruction term of (row m, this column range)
   // ReLU-mask rows (dgrad): 64 bytes per thread and 32 columns, software-pipelined one chunk ahead; the first chunk is
   // requested BEFORE waiting for the accumulator, so its DRAM / L2 latency hides behind the main loop
   auto load_mask = [&](int n, uint4 (&mk)[4]) {
@@ -244,6 +246,19 @@ __device__ __forceinline__ void epilogue_warp_cols(uint32_t taddr, int col_begin
   };
   uint4 mk_next[4];
   if (MASK && col_begin < col_end) load_mask(n0 + col_begin, mk_next);
+  // RECON: the targets of the same 32 columns (32 bytes, or 128 as fp32), pipelined the same way
+  const bool x_u8 = RECON && ep.rx_dtype == DMVAE_U8;
+  const char* xrow = RECON ? reinterpret_cast<const char*>(ep.rx) + (int64_t)m * ep.rx_ld * (x_u8 ? 1 : 4) : nullptr;
+  auto load_x = [&](int n, uint4 (&xr)[8]) {
+    const int per = x_u8 ? 16 : 4, cnt = x_u8 ? 2 : 8;    // elements per 16-byte load, loads per chunk
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      xr[q] = make_uint4(0u, 0u, 0u, 0u);
+      if (q < cnt && m_ok && n + per * q < ep.rx_D) xr[q] = __ldg(reinterpret_cast<const uint4*>(xrow + (int64_t)n * (x_u8 ? 1 : 4)) + q);
+    }
+  };
+  uint4 xr_next[8];
+  if (RECON && col_begin < col_end) load_x(n0 + col_begin, xr_next);
   if (wait_bar != 0) {
     mbar_wait(wait_bar, wait_parity);
     tcgen05_fence_after();
@@ -284,7 +299,67 @@ __device__ __forceinline__ void epilogue_warp_cols(uint32_t taddr, int col_begin
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
       }
-      if (!RELU && !MASK && ep.act == DMVAE_ACT_SIGMOID) {          // reconstructed_X = sigmoid(decoded_X), base_models.py:295-296
+      if (RECON) {
+        // v holds the fp32 decoder logits of (row m, columns n .. n+31): replace them by the gradient of the reconstruction
+        // term and add the term itself to r_row (define_recon_loss, base_models.py:72-85; arithmetic of recon8_t in
+        // elbo.cu: one tanh per element, the log term as a running product folded once per 32 columns)
+        float x[32];
+        const int D = ep.rx_D;
+        uint4 xr[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) xr[q] = xr_next[q];
+        if (c0 + sub + 32 < col_end) load_x(n + 32, xr_next);
+        if (x_u8) {
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            const uint32_t ww[4] = {xr[q].x, xr[q].y, xr[q].z, xr[q].w};
+            // byte -> float without I2F: 0x4B0000bb is the float 2^23 + bb
+            const float xs = ep.rx_scale, xo = -8388608.f * xs;
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              x[16 * q + i] = fmaf(__uint_as_float(__byte_perm(ww[i >> 2], 0x4B000000u, 0x7440u | (uint32_t)(i & 3))), xs, xo);
+          }
+        } else {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            x[4 * q] = __uint_as_float(xr[q].x); x[4 * q + 1] = __uint_as_float(xr[q].y);
+            x[4 * q + 2] = __uint_as_float(xr[q].z); x[4 * q + 3] = __uint_as_float(xr[q].w);
+          }
+        }
+        const float sc = ep.rx_s;
+        float acc = 0.f, prod = 1.f;
+        int nvalid = 0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const bool ok = m_ok && n + j < D;
+          const float d = v[j];
+          float g = 0.f;
+          if (ep.rx_input == DMVAE_INPUT_BINARY) {
+            const float xc = x[j] - 0.5f, h = 0.5f * fabsf(d);
+            float ua;
+            asm("tanh.approx.f32 %0, %1;" : "=f"(ua) : "f"(h));
+            const float u = __uint_as_float((__float_as_uint(d) & 0x80000000u) | __float_as_uint(ua));
+            g = sc * fmaf(0.5f, u, -xc);                  // sigmoid(d) - x = u / 2 - (x - 1/2)
+            if (ok) {
+              acc += fmaf(-d, xc, h);                     // max(d,0) - d x = |d|/2 - d (x - 1/2)
+              prod = fmaf(prod, ua, prod);                // log1p(e^{-|d|}) = ln 2 - ln(1 + u)
+              ++nvalid;
+            }
+          } else {
+            const float df = d - x[j];                    // base_models.py:80-83
+            g = sc * df;
+            if (ok) acc = fmaf(0.5f * df, df, acc);
+          }
+          v[j] = ok ? g : 0.f;                            // padding columns of d_decoded are zero
+        }
+        if (ep.rx_input == DMVAE_INPUT_BINARY) {
+          float lp;
+          asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lp) : "f"(prod));
+          acc += 0.6931471805599453f * ((float)nvalid - lp);
+        }
+        r_row += acc;
+      }
+      if (!RELU && !MASK && !RECON && ep.act == DMVAE_ACT_SIGMOID) {          // reconstructed_X = sigmoid(decoded_X), base_models.py:295-296
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __fdividef(1.f, 1.f + __expf(-v[j]));
       }
@@ -349,6 +424,7 @@ __device__ __forceinline__ void epilogue_warp_cols(uint32_t taddr, int col_begin
     }
     if (FUSE && !OUT_BF16 && n0 + c0 == 0) fused_reparam_row(stage, lane, m_base + lane, M, *fuse);
   }
+  if (RECON && m_ok && col_begin < col_end) ep.r_part[(int64_t)m * ep.r_parts + (n0 + col_begin) / part_w] = r_row;
   if (arrive_bar != 0 && !arrived) {                      // nothing to drain (tile column range beyond N)
     tcgen05_fence_before();
     __syncwarp();
@@ -358,7 +434,8 @@ __device__ __forceinline__ void epilogue_warp_cols(uint32_t taddr, int col_begin
   __syncwarp();
 }
 
-// warp-uniform dispatch to the specialised epilogues
+// warp-uniform dispatch to the specialised epilogues (WITH_RECON: compile the fused-reconstruction variant in)
+template <bool WITH_RECON = true>
 __device__ __forceinline__ void epilogue_warp(uint32_t taddr, int col_begin, int col_end, int m_base, int n0, int M, int N,
                                               const CUtensorMap* tmC, const EpiParams& ep, bool first_split, uint32_t stage,
                                               int lane, uint32_t arrive_bar, const dmvae_reparam_args* fuse = nullptr,
@@ -366,7 +443,10 @@ __device__ __forceinline__ void epilogue_warp(uint32_t taddr, int col_begin, int
   const bool relu = ep.act == DMVAE_ACT_RELU, mask = ep.mask != nullptr;
 #define EPI_GO(B, R, K) epilogue_warp_cols<B, R, K>(taddr, col_begin, col_end, m_base, n0, M, N, tmC, ep, first_split, stage, lane, arrive_bar, nullptr, wait_bar, wait_parity)
   if (ep.out_dtype == DMVAE_BF16) {
-    if (mask) EPI_GO(true, false, true);                  // dgrad (activation already applied upstream)
+    if (WITH_RECON && ep.rx != nullptr)                   // output layer with the reconstruction term fused (dmvae_recon_fuse)
+      epilogue_warp_cols<true, false, false, false, true>(taddr, col_begin, col_end, m_base, n0, M, N, tmC, ep, first_split, stage,
+                                                          lane, arrive_bar, nullptr, wait_bar, wait_parity);
+    else if (mask) EPI_GO(true, false, true);             // dgrad (activation already applied upstream)
     else if (relu) EPI_GO(true, true, false);             // forward hidden layer
     else EPI_GO(true, false, false);
   } else {

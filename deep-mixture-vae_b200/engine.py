@@ -463,6 +463,7 @@ class Engine:
         self.gumbel_in = z(self.K, f32)
         self.zeta = z(self.K, f32)
         self.per_sample = z(4, f32)
+        self.r_part = z((pad_dim(self.D) + 31) // 32, f32)             # fused reconstruction term: one slot per column range
         self.qc = z(self.K, f32)
         self.argmax = torch.zeros(B, dtype=torch.int32, device=dev)
         self.dmean_kl = z(self.L, f32)
@@ -800,12 +801,44 @@ class Engine:
             self._logits_unfolded = False
         _abi.check(self.lib.dmvae_reparam_fwd(self.ctx, C.byref(ra), self._stream()))
 
-    def decode(self, rows: int):
+    def decode(self, rows: int, recon=None):
+        """Decoder MLP.  recon = (X, x_dtype, scale): the output layer's epilogue computes the reconstruction term and
+        writes its gradient to d_decoded instead of the logits to decoded (dmvae_recon_fuse)."""
         a = self.zb
         for nm in self.dec_chain:
             self._fwd(nm, a, a.stride(0), self.act[nm], self.dt, _abi.ACT_RELU, rows)
             a = self.act[nm]
-        self._fwd("decx", a, a.stride(0), self.decoded, self.dec_dt, _abi.ACT_NONE, rows)
+        if recon is None:
+            self._fwd("decx", a, a.stride(0), self.decoded, self.dec_dt, _abi.ACT_NONE, rows)
+            return
+        X, xdt, scale = recon
+        ly = self.layers["decx"]
+        rf = _abi.ReconFuse()
+        rf.X, rf.x_dtype, rf.ldx, rf.x_scale = X.data_ptr(), xdt, X.stride(0), self.x_scale
+        rf.input_type = _abi.INPUT_BINARY if self.input_type == "binary" else _abi.INPUT_REAL
+        rf.scale, rf.D = scale, self.D
+        rf.r_part, rf.r_parts = self.r_part.data_ptr(), self.r_part.shape[1]
+        e = _abi.GemmEpilogue()
+        e.out_dtype, e.act, e.n_valid, e.n_block, e.pad_one, e.split_k = BF16, _abi.ACT_NONE, ly.n_valid, ly.n_block, 1.0, 1
+        e.recon = C.pointer(rf)
+        t0 = self._tic("gemm")
+        _abi.check(self.lib.dmvae_gemm(self.ctx, self.dt, 0, 0, a.data_ptr(), a.stride(0), self.W("decx", op=True).data_ptr(),
+                                       ly.out_pad, self.ddecoded.data_ptr(), self.ddecoded.stride(0), rows, ly.out_pad,
+                                       ly.in_pad, C.byref(e), self._stream()))
+        self._toc("gemm", t0)
+
+    # The reconstruction term in the output layer's epilogue (SURVEY 8 row "fused ELBO"): the decoder logits never reach
+    # HBM, the latent part of the ELBO runs beside the decoder's forward pass.  DMVAE_FUSE_RECON=0 turns it off.
+    fuse_recon = os.environ.get("DMVAE_FUSE_RECON", "1") != "0"
+
+    def _fuse_ok(self, X: torch.Tensor, xdt: int) -> bool:
+        if self.dt != BF16 or self.dec_dt != BF16 or (self.model == "dmvae" and self.cluster_sample):
+            return False
+        if self.K > 128 or self.L > 128:             # the latent-only kernels (row tile, split-tf32 MMA) stop there
+            return False
+        unit = {_abi.U8: 16, F32: 4}.get(xdt)
+        return (unit is not None and self.D % unit == 0 and X.stride(0) % unit == 0 and X.data_ptr() % 16 == 0
+                and X.stride(1) == 1)
 
     def reconstruct(self, rows: int) -> torch.Tensor:
         """reconstructed_X (base_models.py:295-300) of the rows last decoded: the output layer once more with the sigmoid
@@ -934,21 +967,44 @@ class Engine:
         ea.x_scale = self.x_scale
         return ea
 
-    def elbo(self, X, xdt, rows, kl_ratio=1.0, inv_global_batch=None, recon_scale=1.0, prior_grads=True, klr_dev=None,
-             d_gate_extra=None):
-        """Fused ELBO forward + backward and its cross-sample reductions."""
+    def elbo_latent_fork(self, X, xdt, rows, kl_ratio=1.0, inv_global_batch=None, recon_scale=1.0, klr_dev=None,
+                         prior_grads=True):
+        """Fused-reconstruction step, first half: clear the r_part slots and run the LATENT part of the ELBO and the
+        prior-table partial sums on the side stream (they need the encoder heads and the noise only, so they overlap
+        the decoder).  Returns the argument block elbo(fused=...) completes the pass with."""
         s = (1.0 / rows) if inv_global_batch is None else inv_global_batch
         ea = self._elbo_args(X, xdt, rows, kl_ratio, s, recon_scale, klr_dev)
+        ea.r_part, ea.r_parts = self.r_part.data_ptr(), self.r_part.shape[1]
+        gm = self.table("means", grad=True).data_ptr() if prior_grads else None
+        gl = self.table("log_vars", grad=True).data_ptr() if prior_grads else None
+
+        def run():
+            _abi.check(self.lib.dmvae_zero_f32(self.ctx, self.r_part.data_ptr(), rows * self.r_part.shape[1], self._stream()))
+            t0 = self._tic("elbo")
+            _abi.check(self.lib.dmvae_elbo_fwd_bwd(self.ctx, C.byref(ea), self._stream()))
+            self._toc("elbo", t0)
+            _abi.check(self.lib.dmvae_elbo_reduce_stage(self.ctx, C.byref(ea), gm, gl, 0, self.loss_out.data_ptr(),
+                                                        self.red_ws.data_ptr(), 1, self._stream()))
+        self._fork(run)
+        return ea
+
+    def elbo(self, X, xdt, rows, kl_ratio=1.0, inv_global_batch=None, recon_scale=1.0, prior_grads=True, klr_dev=None,
+             d_gate_extra=None, fused=None):
+        """Fused ELBO forward + backward and its cross-sample reductions."""
+        s = (1.0 / rows) if inv_global_batch is None else inv_global_batch
+        ea = fused if fused is not None else self._elbo_args(X, xdt, rows, kl_ratio, s, recon_scale, klr_dev)
         if d_gate_extra is not None:
             ea.d_gate_extra, ea.ld_dge = d_gate_extra.data_ptr(), d_gate_extra.stride(0)
         self._join()
-        t0 = self._tic("elbo")
-        _abi.check(self.lib.dmvae_elbo_fwd_bwd(self.ctx, C.byref(ea), self._stream()))
-        self._toc("elbo", t0)
+        if fused is None:
+            t0 = self._tic("elbo")
+            _abi.check(self.lib.dmvae_elbo_fwd_bwd(self.ctx, C.byref(ea), self._stream()))
+            self._toc("elbo", t0)
         gm = self.table("means", grad=True).data_ptr() if prior_grads else None
         gl = self.table("log_vars", grad=True).data_ptr() if prior_grads else None
-        self._fork(lambda: _abi.check(self.lib.dmvae_elbo_reduce(self.ctx, C.byref(ea), gm, gl, 0, self.loss_out.data_ptr(),
-                                                                 self.red_ws.data_ptr(), self._stream())))
+        stage = 0 if fused is None else 2               # fused: the table partials ran with the latent part
+        self._fork(lambda: _abi.check(self.lib.dmvae_elbo_reduce_stage(self.ctx, C.byref(ea), gm, gl, 0, self.loss_out.data_ptr(),
+                                                                       self.red_ws.data_ptr(), stage, self._stream())))
 
     # ------------------------------------------------------------------------------------------
     # backward
@@ -1166,7 +1222,7 @@ class Engine:
     def forward_backward(self, X: torch.Tensor, rows: int, eps: Optional[torch.Tensor] = None,
                          gumbel: Optional[torch.Tensor] = None, kl_ratio: float = 1.0, inv_global_batch=None,
                          row_offset: int = 0, recon_scale: float = 1.0, backward: bool = True, mode: str = "all",
-                         dev_state: Optional[AdamState] = None):
+                         dev_state: Optional[AdamState] = None, fuse: Optional[bool] = None):
         """encoder -> reparam -> decoder -> fused ELBO (-> gradient GEMMs).  Results stay on the device.
         dev_state: read the Philox step / kl_ratio from device memory (CUDA-graph capture)."""
         if dev_state is None:
@@ -1182,18 +1238,30 @@ class Engine:
                 self.gumbel_in[:rows].copy_(gumbel.reshape(rows, self.K))
         X, xdt = self.stage_input(X, rows)
         sdev = dev_state.state_dev.data_ptr() if dev_state is not None else None
+        klr_dev = self.klr_dev.data_ptr() if (dev_state is not None and mode == "all") else None
+        # fused reconstruction term: the captured training step only by default - decoded_X is not produced, so every
+        # path whose results can be fetched (eager steps, evaluation) keeps the separate ELBO kernel
+        if fuse is None:
+            fuse = self.fuse_recon and backward and dev_state is not None
+        fuse = fuse and self._fuse_ok(X, xdt) and not self._chain_ok(gumbel is not None)
+        fused = None
         if self._chain_ok(gumbel is not None):
             self.forward_chain(rows, eps is not None, row_offset, step_dev=sdev)
         else:
             self.encode(rows, fold_in_reparam=True)
             self.reparam(rows, eps is not None, gumbel is not None, row_offset, step_dev=sdev)
-            self.decode(rows)
+            if fuse:
+                fused = self.elbo_latent_fork(X, xdt, rows, kl_ratio, inv_global_batch, recon_scale, klr_dev,
+                                              prior_grads=(backward and mode == "all"))
+                s = (1.0 / rows) if inv_global_batch is None else inv_global_batch
+                self.decode(rows, recon=(X, xdt, s * recon_scale))
+            else:
+                self.decode(rows)
         flags = dict(all=(True, True, True, True), vae=(True, True, False, True), prior=(False, False, True, False))[mode]
-        klr_dev = self.klr_dev.data_ptr() if (dev_state is not None and mode == "all") else None
         # prior-table gradients only when a full training step will consume them: an evaluation pass (backward=False) or
         # a pre-training mode must leave the means / log_vars gradient slots alone (base_models.py:307-321 never touch them)
         self.elbo(X, xdt, rows, kl_ratio, inv_global_batch, recon_scale, prior_grads=(backward and mode == "all"),
-                  klr_dev=klr_dev)
+                  klr_dev=klr_dev, fused=fused)
         if backward:
             self.backward(rows, train_decoder=flags[0], train_z=flags[1], train_c=flags[2], train_trunk=flags[3])
             self._grads_dirty = True

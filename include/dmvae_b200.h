@@ -68,6 +68,22 @@ int dmvae_ctx_has_tcgen05(const dmvae_ctx* ctx);
  *   DMVAE_BF16: tcgen05.mma (kind::f16, fp32 accumulate in TMEM) fed by TMA   - 2e-2 tier
  *   DMVAE_F32 : fp32 SIMT FFMA tiles                                          - 1e-4 tier
  */
+/* Reconstruction term fused into the OUTPUT layer's GEMM epilogue (define_recon_loss, base_models.py:72-85, and its
+ * gradient): the epilogue holds the fp32 decoder logits d of a tile in registers, reads the targets x of the same
+ * elements, and stores  scale * (sigmoid(d) - x)  (binary) or  scale * (d - x)  (real) in bf16 - the operand of the
+ * decoder's backward GEMMs - INSTEAD of the logits; the per-row sum of the reconstruction term over the column range
+ * one epilogue warp covers (32 to 256 columns, the kernel's choice) goes to its own slot of r_part[row, :], to be added
+ * in a fixed order by dmvae_elbo_reduce.  The caller zero-fills r_part before the GEMM (slots no warp owns stay 0).
+ * bf16 tcgen05 path only, act = NONE, no split-K, not inside dmvae_gemm_chain; columns >= D are stored as 0. */
+typedef struct dmvae_recon_fuse {
+  const void* X; int32_t x_dtype; int64_t ldx;   /* targets [rows, D]: DMVAE_U8 (with x_scale) or DMVAE_F32 */
+  float x_scale;
+  int32_t input_type;                              /* dmvae_input_type */
+  float scale;                                     /* inv_global_batch * recon_scale */
+  int32_t D;
+  float* r_part; int32_t r_parts;                  /* fp32 [rows, r_parts], zero-filled; r_parts >= ceil(N / 32) */
+} dmvae_recon_fuse;
+
 typedef struct dmvae_gemm_epilogue {
   int32_t out_dtype;      /* DMVAE_F32 or DMVAE_BF16 (BF16 only with dtype=BF16) */
   int32_t act;            /* dmvae_act, applied to data columns */
@@ -79,6 +95,7 @@ typedef struct dmvae_gemm_epilogue {
   const float* bias;      /* optional fp32 [N] added before the activation (NULL in the padded layout) */
   int32_t accumulate;     /* 1: C += result (fp32 C only; required when split_k > 1) */
   int32_t split_k;        /* >= 1; partial sums are combined with fp32 red.global.add */
+  const dmvae_recon_fuse* recon;   /* optional (host pointer, read during the call): fuse the reconstruction term */
 } dmvae_gemm_epilogue;
 
 /* C[M,N] = epilogue( op(A) . op(B) );  op(A) is [M,K]: trans_a=0 -> A stored [M,K], 1 -> stored [K,M].
@@ -206,6 +223,10 @@ typedef struct dmvae_elbo_args {
    * mean / log_var and the prior tables together with the ELBO's own gradient. */
   const float* d_gate_extra; int64_t ld_dge;
   float x_scale;           /* uint8 targets: value of one unit (see dmvae_stage_input); 0 means 1 */
+  /* Reconstruction term computed elsewhere (dmvae_recon_fuse in the output layer's GEMM epilogue): with r_parts > 0
+   * dmvae_elbo_fwd_bwd does the LATENT part only (X / decoded / d_decoded are not touched and may be NULL; it can run
+   * before the decoder), and dmvae_elbo_reduce completes per_sample: recon = sum of r_part[row, :] in order. */
+  const float* r_part; int32_t r_parts;
 } dmvae_elbo_args;
 int dmvae_elbo_fwd_bwd(dmvae_ctx* ctx, const dmvae_elbo_args* a, void* stream);
 
@@ -215,6 +236,11 @@ int64_t dmvae_elbo_reduce_workspace(int rows, int L, int K);
 int dmvae_elbo_reduce(dmvae_ctx* ctx, const dmvae_elbo_args* a, float* d_prior_means, float* d_prior_log_vars,
                       int accumulate, float* loss_out /* [4]: recon, KL_c, KL_z, loss (x inv_global_batch) */,
                       float* workspace, void* stream);
+/* The same reduction in two launches, for the fused reconstruction term (r_part): stage 1 = the prior-table partial sums
+ * (needs the latent part's outputs only: it can run beside the decoder), stage 2 = complete per_sample from r_part, the
+ * loss terms and the final table sums (after the output layer's GEMM).  stage 0 = dmvae_elbo_reduce. */
+int dmvae_elbo_reduce_stage(dmvae_ctx* ctx, const dmvae_elbo_args* a, float* d_prior_means, float* d_prior_log_vars,
+                            int accumulate, float* loss_out, float* workspace, int stage, void* stream);
 
 /* ---- MoE expert head (models.py:76-111, :149-163) ------------------------------------------- */
 typedef struct dmvae_moe_args {

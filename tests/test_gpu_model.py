@@ -48,11 +48,12 @@ def _data(B, D, L, K, seed=1, binary=True):
     return X, eps, gum
 
 
-def _compare(cfg, eng, V, X, eps, gum, tol, kl_ratio=1.0, argmax_exact=True, round_fn=None, cap=6e-2, total_tol=None):
+def _compare(cfg, eng, V, X, eps, gum, tol, kl_ratio=1.0, argmax_exact=True, round_fn=None, cap=6e-2, total_tol=None,
+             fuse=None):
     B = len(X)
     out, g = rg.loss_and_grads(cfg, V, X, eps, kl_ratio=kl_ratio, gumbel=gum, temperature=0.7, gemm_round=round_fn)
     Xd = torch.tensor(X, device="cuda")
-    eng.forward_backward(Xd, B, torch.tensor(eps, device="cuda"), torch.tensor(gum, device="cuda"), kl_ratio)
+    eng.forward_backward(Xd, B, torch.tensor(eps, device="cuda"), torch.tensor(gum, device="cuda"), kl_ratio, fuse=fuse)
     torch.cuda.synchronize()
     ps = eng.per_sample[:B].cpu().numpy()
     ref_ps = np.stack([out["recon_ps"], out["kl_c_ps"], out["kl_z_ps"], out["elbo_ps"]], 1)
@@ -124,18 +125,20 @@ def test_vade_fp32_step_matches_oracle():
     eng.close()
 
 
-def test_dmvae_bf16_step_matches_oracle():
+@pytest.mark.parametrize("fuse", [False, True])      # True: reconstruction term in the output layer's epilogue
+def test_dmvae_bf16_step_matches_oracle(fuse):
     cfg, eng, V = _make("dmvae", "bf16")
     X, eps, gum = _data(256, 784, 10, 10)
-    worst = _compare(cfg, eng, V, X, eps, gum, 2e-2, argmax_exact=False)
+    worst = _compare(cfg, eng, V, X, eps, gum, 2e-2, argmax_exact=False, fuse=fuse)
     print("bf16 tier worst gradient rel err %.3g" % worst)
     eng.close()
 
 
-def test_vade_bf16_step_matches_oracle():
+@pytest.mark.parametrize("fuse", [False, True])
+def test_vade_bf16_step_matches_oracle(fuse):
     cfg, eng, V = _make("vade", "bf16", L=64, K=50, B=512)
     X, eps, gum = _data(512, 784, 64, 50)
-    _compare(cfg, eng, V, X, eps, gum, 2e-2, argmax_exact=False)
+    _compare(cfg, eng, V, X, eps, gum, 2e-2, argmax_exact=False, fuse=fuse)
     eng.close()
 
 
@@ -324,3 +327,47 @@ def test_pretrain_modes_match_oracle():
         if name not in c_vars:
             assert np.abs(eng.get_variable(name, grad=True)).max() == 0, name     # var_list restricts the update (:312-321)
     eng.close()
+
+
+@pytest.mark.parametrize("model,D,L,K,B,xkind", [
+    ("dmvae", 784, 10, 10, 256, "u8"),          # row-tile latent kernel, uint8 0/1 targets
+    ("dmvae", 784, 10, 10, 1000, "f32"),        # ragged last row block
+    ("vade", 784, 64, 50, 512, "u8"),           # split-tf32 latent kernel
+    ("dmvae", 3072, 128, 100, 300, "u8s"),      # soft targets byte / 255 (CIFAR-shaped), split-tf32 latent kernel
+    ("dmvae", 96, 10, 10, 130, "real"),         # squared-error reconstruction term
+])
+def test_fused_reconstruction_epilogue_matches_separate_elbo_kernel(model, D, L, K, B, xkind):
+    """The output layer's epilogue computing the reconstruction term (dmvae_recon_fuse) + the latent-only ELBO launch
+    give the step the separate ELBO kernel gives: per-sample terms, loss, d_decoded and every gradient."""
+    input_type = "real" if xkind == "real" else "binary"
+    kw = dict(trunk=(2000, 2000), head=4000, decoder=(4000, 2000, 2000)) if D == 3072 else {}
+    cfg, eng, V = _make(model, "bf16", D=D, L=L, K=K, B=B, input_type=input_type, **kw)
+    rs = np.random.RandomState(3)
+    if xkind == "u8":
+        X = torch.tensor((rs.uniform(size=(B, D)) < 0.1307).astype(np.uint8), device="cuda")
+    elif xkind == "u8s":
+        X = torch.tensor(rs.randint(0, 256, size=(B, D)).astype(np.uint8), device="cuda")
+        eng.x_scale = 1.0 / 255.0
+    else:
+        X = torch.tensor(rs.uniform(size=(B, D)).astype(np.float32), device="cuda")
+    eps = torch.tensor(rs.randn(B, L).astype(np.float32), device="cuda")
+    res = []
+    for fuse in (False, True):
+        eng.zero_grads()
+        eng.per_sample.zero_()
+        eng.ddecoded.zero_()
+        eng.forward_backward(X, B, eps, None, 0.7, fuse=fuse)
+        torch.cuda.synchronize()
+        res.append(dict(ps=eng.per_sample[:B].cpu().numpy().copy(), loss=eng.loss_out.cpu().numpy().copy(),
+                        dd=eng.ddecoded[:B].float().cpu().numpy().copy(), g=eng.grads.cpu().numpy().copy(),
+                        am=eng.argmax[:B].cpu().numpy().copy(), qc=eng.qc[:B].cpu().numpy().copy()))
+    a, b = res
+    assert np.array_equal(a["am"], b["am"]) and np.array_equal(a["qc"], b["qc"])
+    assert relerr(b["ps"][:, 1:3], a["ps"][:, 1:3]) < 1e-5                    # same latent arithmetic (separately compiled)
+    # the reconstruction term: from the fp32 accumulators (fused) vs from the bf16-rounded logits (separate kernel)
+    assert relerr(b["ps"][:, 0], a["ps"][:, 0]) < 2e-3
+    assert relerr(b["ps"][:, 3], a["ps"][:, 3]) < 2e-3
+    assert relerr(b["loss"], a["loss"]) < 5e-4
+    assert (b["dd"][:, D:] == 0).all()
+    assert rel_l2(b["dd"], a["dd"]) < 1e-2                                    # both are bf16 roundings of the same gradient
+    assert rel_l2(b["g"], a["g"]) < 1e-2
