@@ -124,6 +124,7 @@ SIGNATURES = {
     "dmvae_adam": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_void_p, c_float,
                            c_float, c_float, c_float, c_int, c_void_p]),
     "dmvae_step_tick": (c_int, [c_void_p, c_void_p, c_float, c_float, c_float, c_void_p]),
+    "dmvae_log_append": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, C.c_uint64, c_void_p]),
     "dmvae_argmax_contingency": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_int, c_void_p,
                                          c_void_p, c_void_p]),
     "dmvae_dp_reduce_adam": (c_int, [c_void_p, c_int, c_int, C.POINTER(c_void_p), C.POINTER(c_void_p),

@@ -291,8 +291,21 @@ extern "C" int dmvae_gather_rows(dmvae_ctx* ctx, const void* src, int64_t src_pi
                    ((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 15) == 0;
   const int vpr = row_bytes / (v16 ? 16 : 4);
   const int64_t total = (int64_t)rows * vpr;
-  // ONE block per SM: with more, the blocks' registers crowd out the GEMM CTA of the training step running beside them
-  const int blocks = (int)min((int64_t)ctx->sm_count, (total + 511) / 512);
+  // 32 blocks of 128 threads, four 16-byte loads in flight each (256 KB outstanding): enough to keep the bus busy (88 us
+  // for 3.2 MB of host rows instead of 76 us with a block on every SM).  A deeper queue of host reads stalls the training
+  // step running beside it: with a block on every SM the step's first launches start ~60 us late whenever the gather
+  // got going first (scripts/epoch_timeline.py: 362 us per end-to-end step with 148 blocks, 345 us with 32, 351 us with 8).
+  // DMVAE_GATHER_BLOCKS overrides the cap (measurements).
+  int blocks = (int)min((int64_t)ctx->sm_count, (total + 511) / 512);
+  {
+    static int cap = -1;
+    if (cap < 0) {
+      const char* e = getenv("DMVAE_GATHER_BLOCKS");
+      cap = e ? atoi(e) : 32;
+      if (cap <= 0) cap = ctx->sm_count;
+    }
+    blocks = min(blocks, cap);
+  }
   cudaStream_t st = (cudaStream_t)stream;
   // An SM whose shared-memory carveout was configured for this kernel (0 bytes: maximum L1) must drain before a
   // tcgen05 GEMM CTA (~200 KB of shared memory) can be placed on it - the step's GEMM launches then wait for the whole
@@ -434,6 +447,24 @@ __global__ void step_tick_kernel(StepState* st, float lr, float b1, float b2) {
 extern "C" int dmvae_step_tick(dmvae_ctx* ctx, void* state_dev, float lr, float beta1, float beta2, void* stream) {
   DMVAE_CHECK_ARG(ctx && state_dev, "dmvae_step_tick: NULL argument");
   dmvae_launch(step_tick_kernel, dim3(1), dim3(32), 0, (cudaStream_t)stream, true, (StepState*)state_dev, lr, beta1, beta2);
+  DMVAE_LAUNCH_CHECK(ctx);
+  return DMVAE_OK;
+}
+
+// Per-step scalars into a ring indexed by the step counter: the end-to-end loop reads the epoch's losses once, after its
+// last step, instead of queueing a copy between two step graphs.
+__global__ void log_append_kernel(const float* __restrict__ src, int n, float* __restrict__ ring, int cap, const StepState* st,
+                                  unsigned long long step) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const unsigned long long s = st ? st->step : step;
+  if ((int)threadIdx.x < n) ring[(s % (unsigned long long)cap) * n + threadIdx.x] = src[threadIdx.x];
+}
+extern "C" int dmvae_log_append(dmvae_ctx* ctx, const float* src, int n, float* ring, int cap, const void* state_dev,
+                                uint64_t step, void* stream) {
+  DMVAE_CHECK_ARG(ctx && src && ring && n > 0 && n <= 32 && cap > 0, "dmvae_log_append: bad arguments");
+  dmvae_launch(log_append_kernel, dim3(1), dim3(32), 0, (cudaStream_t)stream, true, src, n, ring, cap, (const StepState*)state_dev,
+               (unsigned long long)step);
   DMVAE_LAUNCH_CHECK(ctx);
   return DMVAE_OK;
 }

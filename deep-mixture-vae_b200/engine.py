@@ -473,6 +473,9 @@ class Engine:
         self.f_scratch = z(2 * self.L, f32)
         if getattr(self, "loss_out", None) is None:
             self.loss_out = torch.zeros(4, dtype=f32, device=dev)      # allocated once: fetches keep reading the same scalar block
+            # loss terms of the last LOSS_RING steps, slot = step counter % LOSS_RING (dmvae_log_append): run_epoch reads an
+            # epoch's losses from here after its last step
+            self.loss_ring = torch.zeros(self.LOSS_RING, 4, dtype=f32, device=dev)
         ws = int(self.lib.dmvae_elbo_reduce_workspace(B, self.L, self.K))
         self.red_ws = torch.zeros(max(ws, 4), dtype=f32, device=dev)
         self.x_stage: Dict[int, torch.Tensor] = {}
@@ -488,6 +491,8 @@ class Engine:
             self.moe_dinp = z(self.layers["moe"].in_pad, f32)
             self.y_buf = z(O, f32)
             self.moe_loss = torch.zeros(2, dtype=f32, device=dev)
+
+    LOSS_RING = 4096
 
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
@@ -517,6 +522,7 @@ class Engine:
 
     # CUDA-event timers on the launching stream (bench.py): timers = {"elbo": [], "gemm": [] ...}
     timers = None
+    _log_step = None
 
     def _tic(self, key):
         if self.timers is None or key not in self.timers:
@@ -1003,8 +1009,15 @@ class Engine:
         gm = self.table("means", grad=True).data_ptr() if prior_grads else None
         gl = self.table("log_vars", grad=True).data_ptr() if prior_grads else None
         stage = 0 if fused is None else 2               # fused: the table partials ran with the latent part
-        self._fork(lambda: _abi.check(self.lib.dmvae_elbo_reduce_stage(self.ctx, C.byref(ea), gm, gl, 0, self.loss_out.data_ptr(),
-                                                                       self.red_ws.data_ptr(), stage, self._stream())))
+        log = self._log_step                            # (state_dev pointer | None, host step): also file the loss terms in the ring
+
+        def reduce():
+            _abi.check(self.lib.dmvae_elbo_reduce_stage(self.ctx, C.byref(ea), gm, gl, 0, self.loss_out.data_ptr(),
+                                                        self.red_ws.data_ptr(), stage, self._stream()))
+            if log is not None:
+                _abi.check(self.lib.dmvae_log_append(self.ctx, self.loss_out.data_ptr(), 4, self.loss_ring.data_ptr(),
+                                                     self.LOSS_RING, log[0], log[1], self._stream()))
+        self._fork(reduce)
 
     # ------------------------------------------------------------------------------------------
     # backward
@@ -1431,8 +1444,10 @@ class Engine:
             # shared-memory attributes), then capture the same sequence for every later step
             inv, off = self._dp_scale(rows)
             self._dp_opt = (opt, False) if mode == "all" else None
+            self._log_step = (None, self.step_count)
             self.forward_backward(X, rows, None, None, kl_ratio, inv, off, recon_scale, True, mode)
             self._dp_opt = None
+            self._log_step = None
             self._update(opt)
             self.step_count += 1
             torch.cuda.current_stream(self.device).synchronize()
@@ -1454,7 +1469,9 @@ class Engine:
                 if (self.stream_adam and mode == "all" and self.timers is None and self.overlap
                         and (self.dp is None or self.dp.can_stream())):
                     self._adam_live = (opt, [])
+                self._log_step = (opt.state_dev.data_ptr(), 0)
                 self.forward_backward(X, rows, None, None, kl_ratio, inv, off, recon_scale, True, mode, dev_state=opt)
+                self._log_step = None
                 self._dp_opt = None
                 if self._adam_live is not None:
                     self._adam_rest(opt)
@@ -1527,6 +1544,8 @@ class Engine:
                 self._perm_dev[:N].copy_(self._perm_pin[:N], non_blocking=True)
             perm_dev = self._perm_dev
         row_bytes = host.shape[1] * host.element_size()
+        ring = nb <= self.LOSS_RING and self.use_graphs and os.environ.get("DMVAE_LOSS_RING", "1") != "0"
+        slots = []
         klr, rs = kl_ratio, 1.0
         if mode == "vae":
             klr = 0.0
@@ -1547,9 +1566,21 @@ class Engine:
                                                           rows, row_bytes, C.c_void_p(self._copy_stream.cuda_stream)))
                 self._ready[b].record(self._copy_stream)
             cur.wait_event(self._ready[b])
+            if ring and not slots:
+                slots.append(self.step_count % self.LOSS_RING)
             self.train_step(self._stage[b], rows, opt, None, None, klr, mode, rs)
-            self._loss_log[i].copy_(self.loss_out, non_blocking=True)
+            if not ring:
+                self._loss_log[i].copy_(self.loss_out, non_blocking=True)
             self._free[b].record(cur)
+        if ring:
+            # the steps filed their loss terms in the ring themselves (slot = step counter): one gather after the last step
+            # (consecutive slots: one or two slices, no index upload - that would make the host wait for the epoch here,
+            # before while_busy)
+            first = slots[0]
+            n1 = min(nb, self.LOSS_RING - first)
+            self._loss_log[:n1].copy_(self.loss_ring[first:first + n1], non_blocking=True)
+            if n1 < nb:
+                self._loss_log[n1:nb].copy_(self.loss_ring[:nb - n1], non_blocking=True)
         self._loss_host[:nb].copy_(self._loss_log[:nb], non_blocking=True)
         if while_busy is not None:
             while_busy()                           # host work hidden behind the queued steps (e.g. the next epoch's shuffle)

@@ -282,6 +282,10 @@ int dmvae_adam(dmvae_ctx* ctx, float* params, float* grads, float* m, float* v, 
 /* Per-step device state for CUDA-graph replay: state = {uint64 step; uint32 t; float lr_t}.  One tiny kernel:
  * step += 1, t += 1, lr_t = lr sqrt(1-beta2^t)/(1-beta1^t) (double precision). */
 int dmvae_step_tick(dmvae_ctx* ctx, void* state_dev, float lr, float beta1, float beta2, void* stream);
+/* ring[(step % cap) * n + j] = src[j], j < n <= 32: step read from state_dev (the block dmvae_step_tick advances) when it is
+ * not NULL, else the argument.  Lets a captured step log its loss terms without a copy between two graph launches. */
+int dmvae_log_append(dmvae_ctx* ctx, const float* src, int n, float* ring, int cap, const void* state_dev, uint64_t step,
+                     void* stream);
 
 /* ---- evaluation helpers (get_accuracy, base_models.py:425-432; utils.py:22-34) -------------- */
 /* argmax over K of fp32 [rows,K] and contingency counts d[cluster, class] += 1 (int32 [K, n_labels]) */
