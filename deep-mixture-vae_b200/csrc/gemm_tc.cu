@@ -124,7 +124,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ===================== epilogue =====================
     const int q = warp & 3;                  // TMEM lane quarter this warp may access
     if (nkb > 0) {
-      epilogue_warp(tmem_base + ((uint32_t)(q * 32) << 16), 0, BN, m0 + q * 32, n0, M, N, &tmC, ep, blockIdx.z == 0,
+      epilogue_warp<false>(tmem_base + ((uint32_t)(q * 32) << 16), 0, BN, m0 + q * 32, n0, M, N, &tmC, ep, blockIdx.z == 0,
                     epi_stage + q * kEpiStageBytes, lane, 0u, nullptr, tmem_full_bar, 0u);
     } else {
       mbar_wait(tmem_full_bar, 0);
@@ -288,7 +288,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       int m_blk, n_blk, kb0, kb1;
       decode(u, m_blk, n_blk, kb0, kb1);
       const uint32_t as = ui & 1u, aph = (ui >> 1) & 1u;
-      epilogue_warp(tmem_base + as * BN + ((uint32_t)(q * 32) << 16), half * (BN / 2), (half + 1) * (BN / 2),
+      epilogue_warp<(A_MN == 0 && B_MN == 1)>(tmem_base + as * BN + ((uint32_t)(q * 32) << 16), half * (BN / 2), (half + 1) * (BN / 2),
                     m_blk * 2 * BM + (int)rank * BM + q * 32, n_blk * BN, M, N, &tmC, ep, kb0 == 0, my_stage, lane,
                     lead_tempty0 + as * 8, nullptr, tfull_bar(as), aph);
     }
@@ -429,6 +429,8 @@ int dmvae_gemm_bf16_tc(dmvae_ctx* ctx, int trans_a, int trans_b, const void* A, 
     DMVAE_CHECK_ARG(epi->out_dtype == DMVAE_BF16 && epi->act == DMVAE_ACT_NONE && epi->split_k <= 1 && !epi->accumulate && !epi->relu_mask &&
                         epi->n_valid >= epi->n_block,
                     "gemm(bf16): the fused reconstruction term needs a plain bf16 output layer (no activation, mask, split-K, padding columns)");
+    DMVAE_CHECK_ARG(!trans_a && !trans_b && M >= 2 * BM && N >= 128 && pair_enabled(),
+                    "gemm(bf16): the fused reconstruction term exists in the CTA-pair forward kernel only (M >= 256, N >= 128, no transposes)");
     DMVAE_CHECK_ARG(r->X && r->r_part && r->D > 0 && r->D <= N && r->r_parts >= (N + 31) / 32 &&
                         (r->input_type == DMVAE_INPUT_BINARY || r->input_type == DMVAE_INPUT_REAL),
                     "gemm(bf16): recon fuse: X, r_part, 0 < D <= N, r_parts >= ceil(N / 32), binary | real");

@@ -246,19 +246,19 @@ __device__ __forceinline__ void epilogue_warp_cols(uint32_t taddr, int col_begin
   };
   uint4 mk_next[4];
   if (MASK && col_begin < col_end) load_mask(n0 + col_begin, mk_next);
-  // RECON: the targets of the same 32 columns (32 bytes, or 128 as fp32), pipelined the same way
+  // RECON: the targets of the same 32 columns.  uint8 targets (32 bytes per thread and chunk) are pipelined like the mask;
+  // fp32 targets (128 bytes) are loaded where they are used - holding two chunks of them would spill
   const bool x_u8 = RECON && ep.rx_dtype == DMVAE_U8;
   const char* xrow = RECON ? reinterpret_cast<const char*>(ep.rx) + (int64_t)m * ep.rx_ld * (x_u8 ? 1 : 4) : nullptr;
-  auto load_x = [&](int n, uint4 (&xr)[8]) {
-    const int per = x_u8 ? 16 : 4, cnt = x_u8 ? 2 : 8;    // elements per 16-byte load, loads per chunk
+  auto load_x8 = [&](int n, uint4 (&xr)[2]) {
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
+    for (int q = 0; q < 2; ++q) {
       xr[q] = make_uint4(0u, 0u, 0u, 0u);
-      if (q < cnt && m_ok && n + per * q < ep.rx_D) xr[q] = __ldg(reinterpret_cast<const uint4*>(xrow + (int64_t)n * (x_u8 ? 1 : 4)) + q);
+      if (m_ok && n + 16 * q < ep.rx_D) xr[q] = __ldg(reinterpret_cast<const uint4*>(xrow + n) + q);
     }
   };
-  uint4 xr_next[8];
-  if (RECON && col_begin < col_end) load_x(n0 + col_begin, xr_next);
+  uint4 xr_next[2];
+  if (RECON && x_u8 && col_begin < col_end) load_x8(n0 + col_begin, xr_next);
   if (wait_bar != 0) {
     mbar_wait(wait_bar, wait_parity);
     tcgen05_fence_after();
@@ -303,59 +303,89 @@ __device__ __forceinline__ void epilogue_warp_cols(uint32_t taddr, int col_begin
         // v holds the fp32 decoder logits of (row m, columns n .. n+31): replace them by the gradient of the reconstruction
         // term and add the term itself to r_row (define_recon_loss, base_models.py:72-85; arithmetic of recon8_t in
         // elbo.cu: one tanh per element, the log term as a running product folded once per 32 columns)
-        float x[32];
         const int D = ep.rx_D;
-        uint4 xr[8];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) xr[q] = xr_next[q];
-        if (c0 + sub + 32 < col_end) load_x(n + 32, xr_next);
+        uint4 xr[2];
         if (x_u8) {
-#pragma unroll
-          for (int q = 0; q < 2; ++q) {
-            const uint32_t ww[4] = {xr[q].x, xr[q].y, xr[q].z, xr[q].w};
-            // byte -> float without I2F: 0x4B0000bb is the float 2^23 + bb
-            const float xs = ep.rx_scale, xo = -8388608.f * xs;
-#pragma unroll
-            for (int i = 0; i < 16; ++i)
-              x[16 * q + i] = fmaf(__uint_as_float(__byte_perm(ww[i >> 2], 0x4B000000u, 0x7440u | (uint32_t)(i & 3))), xs, xo);
-          }
-        } else {
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            x[4 * q] = __uint_as_float(xr[q].x); x[4 * q + 1] = __uint_as_float(xr[q].y);
-            x[4 * q + 2] = __uint_as_float(xr[q].z); x[4 * q + 3] = __uint_as_float(xr[q].w);
-          }
+          xr[0] = xr_next[0]; xr[1] = xr_next[1];
+          if (c0 + sub + 32 < col_end) load_x8(n + 32, xr_next);
         }
         const float sc = ep.rx_s;
-        float acc = 0.f, prod = 1.f;
-        int nvalid = 0;
+        float acc = 0.f;
+        const bool binary = ep.rx_input == DMVAE_INPUT_BINARY;
+        if (x_u8 && binary && n + 32 <= D) {
+          // Interior chunk of the common case (uint8 targets, Bernoulli likelihood), ~10 issue slots per element.
+          // byte -> float without I2F: 0x4700bb00 is the float 32768 + bb (one PRMT), so with xc = x - 1/2:
+          //   xc = fma(f, xs, -(32768 xs + 1/2)),   -s xc = fma(f, -s xs, s (32768 xs + 1/2))
+          //   gradient s (sigmoid(d) - x) = fma(s / 2, u, -s xc),  u = sign(d) tanh(|d| / 2)
+          //   term  max(d,0) - d x + log1p(e^-|d|) = |d| / 2 - d xc + ln 2 - ln(1 + |u|)
+          // Rows >= M compute on zeros and are never stored.
+          const float xs = ep.rx_scale, xo = -(32768.f * xs + 0.5f);
+          const float nsx = -sc * xs, nso = -sc * xo, hs = 0.5f * sc;
+          float accd = 0.f, prod = 1.f;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const bool ok = m_ok && n + j < D;
-          const float d = v[j];
-          float g = 0.f;
-          if (ep.rx_input == DMVAE_INPUT_BINARY) {
-            const float xc = x[j] - 0.5f, h = 0.5f * fabsf(d);
+          for (int jj = 0; jj < 32; ++jj) {
+            const uint32_t w = jj < 16 ? (&xr[0].x)[jj >> 2] : (&xr[1].x)[(jj - 16) >> 2];
+            const float f = __uint_as_float(__byte_perm(w, 0x47000000u, 0x7404u | ((uint32_t)(jj & 3) << 4)));
+            const float d = v[jj];
+            const float xc = fmaf(f, xs, xo), nsxc = fmaf(f, nsx, nso), h = 0.5f * fabsf(d);
             float ua;
             asm("tanh.approx.f32 %0, %1;" : "=f"(ua) : "f"(h));
             const float u = __uint_as_float((__float_as_uint(d) & 0x80000000u) | __float_as_uint(ua));
-            g = sc * fmaf(0.5f, u, -xc);                  // sigmoid(d) - x = u / 2 - (x - 1/2)
-            if (ok) {
-              acc += fmaf(-d, xc, h);                     // max(d,0) - d x = |d|/2 - d (x - 1/2)
-              prod = fmaf(prod, ua, prod);                // log1p(e^{-|d|}) = ln 2 - ln(1 + u)
-              ++nvalid;
-            }
-          } else {
-            const float df = d - x[j];                    // base_models.py:80-83
-            g = sc * df;
-            if (ok) acc = fmaf(0.5f * df, df, acc);
+            v[jj] = fmaf(hs, u, nsxc);
+            acc += h;
+            accd = fmaf(d, xc, accd);
+            prod = fmaf(prod, ua, prod);
           }
-          v[j] = ok ? g : 0.f;                            // padding columns of d_decoded are zero
-        }
-        if (ep.rx_input == DMVAE_INPUT_BINARY) {
           float lp;
           asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lp) : "f"(prod));
-          acc += 0.6931471805599453f * ((float)nvalid - lp);
+          acc = (acc - accd) + 0.6931471805599453f * (32.f - lp);
+        } else {
+          float x[32];
+          if (x_u8) {
+            const float xs = ep.rx_scale, xo = -32768.f * xs;
+#pragma unroll
+            for (int jj = 0; jj < 32; ++jj) {
+              const uint32_t w = jj < 16 ? (&xr[0].x)[jj >> 2] : (&xr[1].x)[(jj - 16) >> 2];
+              x[jj] = fmaf(__uint_as_float(__byte_perm(w, 0x47000000u, 0x7404u | ((uint32_t)(jj & 3) << 4))), xs, xo);
+            }
+          } else {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (m_ok && n + 4 * q < D) w = __ldg(reinterpret_cast<const float4*>(xrow + (int64_t)n * 4) + q);
+              x[4 * q] = w.x; x[4 * q + 1] = w.y; x[4 * q + 2] = w.z; x[4 * q + 3] = w.w;
+            }
+          }
+          float prod = 1.f;
+          int nvalid = 0;
+#pragma unroll
+          for (int jj = 0; jj < 32; ++jj) {
+            const bool ok = m_ok && n + jj < D;
+            const float d = v[jj];
+            float g = 0.f;
+            if (binary) {
+              const float xc = x[jj] - 0.5f, h = 0.5f * fabsf(d);
+              float ua;
+              asm("tanh.approx.f32 %0, %1;" : "=f"(ua) : "f"(h));
+              const float u = __uint_as_float((__float_as_uint(d) & 0x80000000u) | __float_as_uint(ua));
+              g = sc * fmaf(0.5f, u, -xc);                // sigmoid(d) - x = u / 2 - (x - 1/2)
+              if (ok) {
+                acc += fmaf(-d, xc, h);                   // max(d,0) - d x = |d|/2 - d (x - 1/2)
+                prod = fmaf(prod, ua, prod);              // log1p(e^{-|d|}) = ln 2 - ln(1 + u)
+                ++nvalid;
+              }
+            } else {
+              const float df = d - x[jj];                 // base_models.py:80-83
+              g = sc * df;
+              if (ok) acc = fmaf(0.5f * df, df, acc);
+            }
+            v[jj] = ok ? g : 0.f;                         // padding columns of d_decoded are zero
+          }
+          if (binary) {
+            float lp;
+            asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lp) : "f"(prod));
+            acc += 0.6931471805599453f * ((float)nvalid - lp);
+          }
         }
         r_row += acc;
       }

@@ -837,7 +837,9 @@ class Engine:
     # HBM, the latent part of the ELBO runs beside the decoder's forward pass.  DMVAE_FUSE_RECON=0 turns it off.
     fuse_recon = os.environ.get("DMVAE_FUSE_RECON", "1") != "0"
 
-    def _fuse_ok(self, X: torch.Tensor, xdt: int) -> bool:
+    def _fuse_ok(self, X: torch.Tensor, xdt: int, rows: int = 1 << 30) -> bool:
+        if rows < 256 or pad_dim(self.D) < 128:        # the CTA-pair forward kernel carries the fused epilogue
+            return False
         if self.dt != BF16 or self.dec_dt != BF16 or (self.model == "dmvae" and self.cluster_sample):
             return False
         if self.K > 128 or self.L > 128:             # the latent-only kernels (row tile, split-tf32 MMA) stop there
@@ -1256,7 +1258,7 @@ class Engine:
         # path whose results can be fetched (eager steps, evaluation) keeps the separate ELBO kernel
         if fuse is None:
             fuse = self.fuse_recon and backward and dev_state is not None
-        fuse = fuse and self._fuse_ok(X, xdt) and not self._chain_ok(gumbel is not None)
+        fuse = fuse and self._fuse_ok(X, xdt, rows) and not self._chain_ok(gumbel is not None)
         fused = None
         if self._chain_ok(gumbel is not None):
             self.forward_chain(rows, eps is not None, row_offset, step_dev=sdev)

@@ -334,7 +334,7 @@ def test_pretrain_modes_match_oracle():
     ("dmvae", 784, 10, 10, 1000, "f32"),        # ragged last row block
     ("vade", 784, 64, 50, 512, "u8"),           # split-tf32 latent kernel
     ("dmvae", 3072, 128, 100, 300, "u8s"),      # soft targets byte / 255 (CIFAR-shaped), split-tf32 latent kernel
-    ("dmvae", 96, 10, 10, 130, "real"),         # squared-error reconstruction term
+    ("dmvae", 96, 10, 10, 300, "real"),         # squared-error reconstruction term
 ])
 def test_fused_reconstruction_epilogue_matches_separate_elbo_kernel(model, D, L, K, B, xkind):
     """The output layer's epilogue computing the reconstruction term (dmvae_recon_fuse) + the latent-only ELBO launch
