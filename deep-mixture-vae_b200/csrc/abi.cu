@@ -68,6 +68,8 @@ extern "C" int dmvae_ctx_create(int device, dmvae_ctx** out) {
 }
 
 extern "C" int dmvae_ctx_destroy(dmvae_ctx* ctx) {
+  if (ctx)
+    for (auto& kv : ctx->scheds) cudaFree(kv.second);
   delete ctx;
   return DMVAE_OK;
 }

@@ -10,6 +10,7 @@
 #include <string.h>
 
 #include <mutex>
+#include <map>
 #include <unordered_map>
 #include <vector>
 
@@ -45,6 +46,9 @@ struct dmvae_ctx {
   int64_t launches = 0;
   void* encode_tiled = nullptr;  // cuTensorMapEncodeTiled, resolved through the runtime
   std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> tmaps;
+  // unit -> CTA-pair schedules of the grouped GEMM launches (gemm_chain.cu), keyed by the launch's tiling signature;
+  // device arrays [pairs + 1 offsets][unit ids], built at the first (eager) use of a shape and never freed before the context
+  std::map<std::vector<int>, int*> scheds;
   std::mutex mu;
 };
 

@@ -11,6 +11,9 @@
 // (grid <= SM count, one CTA per SM) the schedule cannot deadlock, and the row blocks of consecutive layers overlap.
 // The mechanics per unit (TMA -> smem stages -> tcgen05.mma cta_group::2 -> double-buffered TMEM -> TMA-store
 // epilogue) are those of gemm_tc2_kernel; operand majors, tile width and epilogue are per-layer run-time values.
+#include <algorithm>
+#include <vector>
+
 #include "tc_device.cuh"
 
 namespace {
@@ -18,6 +21,7 @@ namespace {
 constexpr int kMaxChain = 16;
 constexpr int CH_BN = 256;                                   // widest tile (TMEM: 2 x 256 columns)
 constexpr int CH_STAGES = 6;
+constexpr int kMaxSchedUnits = 64;           // longest per-pair unit list a scheduled launch may have (else: round robin)
 constexpr int CH_STAGE_BYTES = A_TILE_BYTES + (CH_BN / 2) * BK * 2;   // 32 KiB
 constexpr size_t CH_SMEM = (size_t)CH_STAGES * CH_STAGE_BYTES + kEpiBytes2 + 1024;
 
@@ -38,6 +42,7 @@ struct ChainLayer {
 
 struct ChainParams {
   int n_layers, n_units, cstride;
+  const int* sched;    // unit schedule [pairs + 1 offsets][unit ids] (build_schedule), or NULL: unit u runs on pair u % pairs
   int* counters;       // [n_layers][cstride], zero at launch
   dmvae_reparam_args ra;
   ChainLayer L[kMaxChain];
@@ -63,6 +68,7 @@ struct Unit {
 };
 
 __device__ __forceinline__ void decode_unit(const ChainParams& P, int u, int& e, Unit& out) {
+  if (P.sched) e = 0;                           // scheduled units come in any order
   while (u >= P.L[e].unit_end) ++e;
   const ChainLayer& Ly = P.L[e];
   const int t = u - Ly.unit_begin;
@@ -82,6 +88,8 @@ gemm_chain_kernel(const __grid_constant__ ChainParams P) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2 * CH_STAGES + 4];
   __shared__ uint32_t tmem_slot;
+  __shared__ int s_units[kMaxSchedUnits];      // this pair's units, in execution order (scheduled launches)
+  __shared__ int s_cnt;
 
   const uint32_t tiles = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t epi_stage = tiles + CH_STAGES * CH_STAGE_BYTES;
@@ -105,6 +113,11 @@ gemm_chain_kernel(const __grid_constant__ ChainParams P) {
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  if (warp == 2 && P.sched) {                  // the table is written once, at the first use of the shape: no need to wait for the predecessor
+    const int b = __ldg(P.sched + pair_id), n = __ldg(P.sched + pair_id + 1) - b;
+    for (int i = lane; i < n; i += 32) s_units[i] = __ldg(P.sched + n_pairs + 1 + b + i);
+    if (lane == 0) s_cnt = n;
+  }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(2 * CH_BN)
                  : "memory");
@@ -116,6 +129,14 @@ gemm_chain_kernel(const __grid_constant__ ChainParams P) {
   const uint32_t tmem_base = tmem_slot;
   pdl_wait();
   pdl_launch_dependents();
+  // this pair's units: its slice of the schedule (longest-processing-time-first, built on the host; copied into shared
+  // memory by warp 2 before the cluster barrier above, so no role waits on a global load per unit), or every n_pairs-th unit
+  int u_begin = pair_id, u_end = P.n_units, u_step = n_pairs;
+  if (P.sched) {
+    u_begin = 0;
+    u_end = s_cnt;
+    u_step = 1;
+  }
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
@@ -123,7 +144,8 @@ gemm_chain_kernel(const __grid_constant__ ChainParams P) {
       const uint32_t lead_full0 = mapa_u32(full_bar(0), 0);
       uint32_t it = 0;
       int e = 0;
-      for (int u = pair_id; u < P.n_units; u += n_pairs) {
+      for (int i = u_begin; i < u_end; i += u_step) {
+        const int u = P.sched ? s_units[i] : i;
         Unit un;
         decode_unit(P, u, e, un);
         const ChainLayer& Ly = P.L[e];
@@ -171,7 +193,8 @@ gemm_chain_kernel(const __grid_constant__ ChainParams P) {
     if (lane == 0 && rank == 0) {
       uint32_t it = 0, ui = 0;
       int e = 0;
-      for (int u = pair_id; u < P.n_units; u += n_pairs, ++ui) {
+      for (int i = u_begin; i < u_end; i += u_step, ++ui) {
+        const int u = P.sched ? s_units[i] : i;
         Unit un;
         decode_unit(P, u, e, un);
         const ChainLayer& Ly = P.L[e];
@@ -206,7 +229,8 @@ gemm_chain_kernel(const __grid_constant__ ChainParams P) {
     const uint32_t my_stage = epi_stage + (uint32_t)(warp - 2) * kEpiStageBytes;
     uint32_t ui = 0;
     int e = 0;
-    for (int u = pair_id; u < P.n_units; u += n_pairs, ++ui) {
+    for (int i = u_begin; i < u_end; i += u_step, ++ui) {
+      const int u = P.sched ? s_units[i] : i;
       Unit un;
       decode_unit(P, u, e, un);
       const ChainLayer& Ly = P.L[e];
@@ -237,6 +261,93 @@ gemm_chain_kernel(const __grid_constant__ ChainParams P) {
 }
 
 }  // namespace
+
+// Units of a grouped launch differ a lot in length (a weight-gradient unit contracts over the batch: 64-128 k-blocks; a
+// data-gradient unit over a layer width: 8-64), and "unit u on pair u % pairs" leaves some pairs with two long units while
+// others hold one short one (modelled makespan up to 1.4x the mean at the 4096-row shapes).  Independent launches therefore
+// get a longest-processing-time-first assignment: units sorted by cost (k-blocks x bytes per k-block + a fixed part for
+// prologue / epilogue), each given to the least-loaded pair.  The table lives in device memory, keyed by the tiling.
+int* build_schedule(dmvae_ctx* ctx, const ChainParams& P, int pairs, bool capturing) {
+  std::vector<int> key;
+  key.push_back(pairs);
+  for (int i = 0; i < P.n_layers; ++i) {
+    const ChainLayer& L = P.L[i];
+    key.insert(key.end(), {L.tiles_m, L.tiles_n, L.nsplit, L.kb_per_split, L.nkb, L.bn});
+  }
+  {
+    std::lock_guard<std::mutex> g(ctx->mu);
+    auto it = ctx->scheds.find(key);
+    if (it != ctx->scheds.end()) return it->second;
+  }
+  if (capturing) return nullptr;              // no allocation inside a capture: round robin (the eager step normally came first)
+  struct U { int cost, id; };
+  std::vector<U> us;
+  us.reserve(P.n_units);
+  for (int i = 0; i < P.n_layers; ++i) {
+    const ChainLayer& L = P.L[i];
+    const int per_split = L.tiles_m * L.tiles_n;
+    for (int t = 0; t < L.unit_end - L.unit_begin; ++t) {
+      const int split = t / per_split;
+      const int kb = std::min(L.nkb, (split + 1) * L.kb_per_split) - split * L.kb_per_split;
+      us.push_back({16 + kb * (L.bn == 256 ? 4 : 3), L.unit_begin + t});     // 8 KB of operands per cost unit; 16 ~ four wide k-blocks
+    }
+  }
+  // what "unit u on pair u % pairs" would give under the same cost model
+  std::vector<long long> rr(pairs, 0);
+  for (const U& u : us) rr[u.id % pairs] += u.cost;
+  const long long rr_makespan = *std::max_element(rr.begin(), rr.end());
+  std::stable_sort(us.begin(), us.end(), [](const U& a, const U& b) { return a.cost > b.cost; });
+  std::vector<std::vector<int>> lists(pairs);
+  std::vector<long long> load(pairs, 0);
+  for (const U& u : us) {
+    int best = 0;
+    for (int p = 1; p < pairs; ++p)
+      if (load[p] < load[best]) best = p;
+    lists[best].push_back(u.id);
+    load[best] += u.cost;
+  }
+  // Keep the plain order unless the schedule shortens the modelled makespan by more than 3 %: where both are equal (most
+  // 4096-row shapes: two units per pair either way) the plain order measured 2 % faster - it runs neighbouring tiles of one
+  // GEMM at the same time on neighbouring pairs.
+  if (*std::max_element(load.begin(), load.end()) * 103 >= rr_makespan * 100) {
+    std::lock_guard<std::mutex> g(ctx->mu);
+    ctx->scheds[key] = nullptr;
+    return nullptr;
+  }
+  // Order inside a pair: the epilogue of a unit overlaps the main loop of the NEXT one (double-buffered accumulators), the
+  // last unit's epilogue is exposed.  So the units with the heavy epilogue (fp32 tiles reduced into the gradient buffer:
+  // 4 bytes x 256 x bn of red.global.add) go first and the bf16 data-gradient tiles last (measured at cfg2: the other
+  // order costs 3 % of the step).
+  auto epi_bytes = [&](int id) {
+    int e = 0;
+    while (id >= P.L[e].unit_end) ++e;
+    return P.L[e].bn * (P.L[e].ep.out_dtype == DMVAE_BF16 ? 2 : 4);
+  };
+  for (int p = 0; p < pairs; ++p)
+    std::stable_sort(lists[p].begin(), lists[p].end(), [&](int a, int b) { return epi_bytes(a) > epi_bytes(b); });
+  for (int p = 0; p < pairs; ++p)
+    if ((int)lists[p].size() > kMaxSchedUnits) {          // very large launches: many units per pair, round robin is balanced enough
+      std::lock_guard<std::mutex> g(ctx->mu);
+      ctx->scheds[key] = nullptr;
+      return nullptr;
+    }
+  std::vector<int> host(pairs + 1 + P.n_units);
+  int off = 0;
+  for (int p = 0; p < pairs; ++p) {
+    host[p] = off;
+    for (int id : lists[p]) host[pairs + 1 + off++] = id;
+  }
+  host[pairs] = off;
+  int* dev = nullptr;
+  if (cudaMalloc(&dev, host.size() * sizeof(int)) != cudaSuccess) return nullptr;
+  if (cudaMemcpy(dev, host.data(), host.size() * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess) {
+    cudaFree(dev);
+    return nullptr;
+  }
+  std::lock_guard<std::mutex> g(ctx->mu);
+  ctx->scheds[key] = dev;
+  return dev;
+}
 
 extern "C" int64_t dmvae_gemm_chain_counters(int n, int max_rows) {
   if (n <= 0 || max_rows <= 0) return 0;
@@ -341,6 +452,16 @@ extern "C" int dmvae_gemm_chain(dmvae_ctx* ctx, const dmvae_chain_gemm* g, int n
   }
   // every pair must be resident at once (units wait for one another): never more pairs than the device holds
   const int pairs = std::max(1, std::min(units, pairs_avail));
+  static int lpt = -1;                       // DMVAE_CHAIN_LPT=0: unit u on pair u % pairs (A/B measurements)
+  if (lpt < 0) {
+    const char* ev = getenv("DMVAE_CHAIN_LPT");
+    lpt = (ev && ev[0] == '0') ? 0 : 1;
+  }
+  if (lpt && !any_dep && units > pairs) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    DMVAE_CUDA(cudaStreamIsCapturing(st, &cs));
+    P.sched = build_schedule(ctx, P, pairs, cs != cudaStreamCaptureStatusNone);
+  }
   DMVAE_CUDA(dmvae_launch(gemm_chain_kernel, dim3(2 * pairs), dim3(kThreads2), CH_SMEM, st, !memset_first, P));
   DMVAE_LAUNCH_CHECK(ctx);
   return DMVAE_OK;
