@@ -491,6 +491,7 @@ class Engine:
             self.moe_dinp = z(self.layers["moe"].in_pad, f32)
             self.y_buf = z(O, f32)
             self.moe_loss = torch.zeros(2, dtype=f32, device=dev)
+            self.moe_ring = torch.zeros(self.LOSS_RING, 2, dtype=f32, device=dev)
 
     LOSS_RING = 4096
 
@@ -523,6 +524,7 @@ class Engine:
     # CUDA-event timers on the launching stream (bench.py): timers = {"elbo": [], "gemm": [] ...}
     timers = None
     _log_step = None
+    _log_moe = None
 
     def _tic(self, key):
         if self.timers is None or key not in self.timers:
@@ -1312,14 +1314,18 @@ class Engine:
         key = ("moe", X.data_ptr(), X.dtype, Y.data_ptr(), rows, id(opt), float(kl_ratio), float(self.x_scale))
         ent = self._graphs.get(key)
         if ent is None:
+            self._log_moe = (None, self.step_count)
             self.moe_step(X, Y, rows, opt, kl_ratio=kl_ratio, graph=False)       # eager: warms descriptor caches
+            self._log_moe = None
             torch.cuda.current_stream(self.device).synchronize()
             g = torch.cuda.CUDAGraph()
             l0 = int(self.lib.dmvae_ctx_launch_count(self.ctx))
             with torch.cuda.graph(g):
                 self._fork(lambda: _abi.check(self.lib.dmvae_step_tick(self.ctx, opt.state_dev.data_ptr(), opt.lr,
                                                                         opt.beta1, opt.beta2, self._stream())))
+                self._log_moe = (opt.state_dev.data_ptr(), 0)
                 self._moe_body(X, Y, rows, False, False, kl_ratio, True, opt)
+                self._log_moe = None
                 self._update(opt, use_dev=True)
             self._graphs[key] = (g, int(self.lib.dmvae_ctx_launch_count(self.ctx)) - l0, False)
             self._grads_dirty = False
@@ -1379,6 +1385,15 @@ class Engine:
         _abi.check(self.lib.dmvae_reduce_columns(self.ctx, self.moe_ps.data_ptr(), 2, rows, 2, 1.0, self.moe_loss.data_ptr(), st()))
         if not train:
             return
+        log = self._log_moe
+        if log is not None:
+            # both loss blocks are final here (the ELBO's reduction was joined above): file them in the rings on the side stream
+            def append():
+                _abi.check(self.lib.dmvae_log_append(self.ctx, self.moe_loss.data_ptr(), 2, self.moe_ring.data_ptr(),
+                                                     self.LOSS_RING, log[0], log[1], self._stream()))
+                _abi.check(self.lib.dmvae_log_append(self.ctx, self.loss_out.data_ptr(), 4, self.loss_ring.data_ptr(),
+                                                     self.LOSS_RING, log[0], log[1], self._stream()))
+            self._fork(append)
         if self.model == "vade":
             # the gate is gamma = get_cluster_probs(Z) (models.py:74, priors.py:91-102): the supervised loss reaches Z, mean,
             # log_var and the prior tables through it.  Second pass of the fused ELBO kernel with d loss / d gamma added
@@ -1628,6 +1643,8 @@ class Engine:
             perm_dev = self._perm_dev
         xb, yb = host_x.shape[1] * host_x.element_size(), O * 4
         cs = C.c_void_p(self._copy_stream.cuda_stream)
+        ring = nb <= self.LOSS_RING and self.use_graphs and os.environ.get("DMVAE_LOSS_RING", "1") != "0"
+        first = 0
         for i in range(nb):
             b = i & 1
             lo = i * batch_size
@@ -1644,10 +1661,21 @@ class Engine:
                     _abi.check(self.lib.dmvae_gather_rows(self.ctx, host_y.data_ptr(), yb, ix, self._stage_y[b].data_ptr(), yb, rows, yb, cs))
                 self._ready[b].record(self._copy_stream)
             cur.wait_event(self._ready[b])
+            if i == 0:
+                first = self.step_count % self.LOSS_RING
             self.moe_step(self._stage[b], self._stage_y[b], rows, opt, kl_ratio=kl_ratio, graph=True)
-            self._moe_log[i, :2].copy_(self.moe_loss, non_blocking=True)
-            self._moe_log[i, 2:].copy_(self.loss_out, non_blocking=True)
+            if not ring:
+                self._moe_log[i, :2].copy_(self.moe_loss, non_blocking=True)
+                self._moe_log[i, 2:].copy_(self.loss_out, non_blocking=True)
             self._free[b].record(cur)
+        if ring and nb > 0:
+            # the captured steps filed their loss blocks in the rings (slot = step counter): consecutive slots, two slices at most
+            n1 = min(nb, self.LOSS_RING - first)
+            self._moe_log[:n1, :2].copy_(self.moe_ring[first:first + n1], non_blocking=True)
+            self._moe_log[:n1, 2:].copy_(self.loss_ring[first:first + n1], non_blocking=True)
+            if n1 < nb:
+                self._moe_log[n1:nb, :2].copy_(self.moe_ring[:nb - n1], non_blocking=True)
+                self._moe_log[n1:nb, 2:].copy_(self.loss_ring[:nb - n1], non_blocking=True)
         self._moe_log_host[:nb].copy_(self._moe_log[:nb], non_blocking=True)
         if while_busy is not None:
             while_busy()
