@@ -107,6 +107,7 @@ SIGNATURES = {
                                    c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "dmvae_stage_input": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_void_p, c_int, c_int64, c_int, c_int, c_float, c_void_p]),
     "dmvae_gather_rows": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p]),
+    "dmvae_gather_rows_bits": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p]),
     "dmvae_reparam_fwd": (c_int, [c_void_p, C.POINTER(ReparamArgs), c_void_p]),
     "dmvae_reparam_bwd": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p,
                                   c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int, c_int64, c_int, c_void_p]),

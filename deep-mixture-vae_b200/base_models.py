@@ -259,6 +259,10 @@ class VAE:
         opt = eng.optimizer(key, self._lr[key])
         data.begin_epoch()                                     # draws the epoch's permutation (utils.py:450-454)
         runner = eng.dp if eng.dp is not None else eng
+        bits = data.host_bits()
+        if bits is not None:                                   # binarised rows: one bit per element over the bus
+            return runner.run_epoch(bits[0], data.batch_size, opt, kl_ratio, mode, perm=data.perm,
+                                    while_busy=data.prefetch_epoch, x_scale=1.0, packed_D=bits[1])
         host = data.host_tensor()
         return runner.run_epoch(host, data.batch_size, opt, kl_ratio, mode, perm=data.perm,
                                 while_busy=data.prefetch_epoch, x_scale=data.host_scale)

@@ -328,6 +328,75 @@ extern "C" int dmvae_gather_rows(dmvae_ctx* ctx, const void* src, int64_t src_pi
   return DMVAE_OK;
 }
 
+// The same gather for {0,1}-valued rows stored ONE BIT per element on the host (little-endian bit order inside a byte,
+// as numpy.packbits(bitorder="little")): 8x fewer bytes over the bus, expanded to one uint8 per element while writing the
+// device batch.  A thread moves 16 packed bytes (128 elements); consecutive threads read consecutive pieces of a row, so
+// a 784-element row is ONE 112-byte request on the bus (a word-per-thread version issued 25 small reads per row and
+// disturbed the training step beside it as much as the 8x larger byte gather).
+__global__ void __launch_bounds__(128, 12) gather_bits_kernel(const uint8_t* __restrict__ src, int64_t src_pitch,
+                                                              const int32_t* __restrict__ idx, uint8_t* __restrict__ dst,
+                                                              int64_t dst_pitch, int rows, int D, int vecs_per_row) {
+  constexpr int U = 2;
+  const int64_t total = (int64_t)rows * vecs_per_row;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  auto expand = [&](const uint4& v, int r, int c) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint8_t* d = dst + (int64_t)r * dst_pitch + 128 * c;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      uint32_t o[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {             // output word q holds bits 4q .. 4q+3 of w[k] as bytes
+        const uint32_t n = (w[k] >> (4 * q)) & 0xfu;
+        o[q] = (n & 1u) | ((n & 2u) << 7) | ((n & 4u) << 14) | ((n & 8u) << 21);
+      }
+      const int e0 = 128 * c + 32 * k;
+      if (e0 + 16 <= D) *reinterpret_cast<uint4*>(d + 32 * k) = make_uint4(o[0], o[1], o[2], o[3]);
+      if (e0 + 32 <= D) *reinterpret_cast<uint4*>(d + 32 * k + 16) = make_uint4(o[4], o[5], o[6], o[7]);
+    }
+  };
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + (U - 1) * stride < total; i += U * stride) {
+    uint4 v[U];
+    int r[U], c[U];
+#pragma unroll
+    for (int j = 0; j < U; ++j) {
+      const int64_t e = i + j * stride;
+      r[j] = (int)(e / vecs_per_row);
+      c[j] = (int)(e - (int64_t)r[j] * vecs_per_row);
+      v[j] = *reinterpret_cast<const uint4*>(src + (int64_t)idx[r[j]] * src_pitch + 16 * c[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < U; ++j) expand(v[j], r[j], c[j]);
+  }
+  for (; i < total; i += stride) {
+    const int r = (int)(i / vecs_per_row), c = (int)(i - (int64_t)r * vecs_per_row);
+    expand(*reinterpret_cast<const uint4*>(src + (int64_t)idx[r] * src_pitch + 16 * c), r, c);
+  }
+}
+
+extern "C" int dmvae_gather_rows_bits(dmvae_ctx* ctx, const void* src_bits, int64_t src_pitch_bytes, const int32_t* idx, void* dst,
+                                      int64_t dst_pitch_bytes, int rows, int D, void* stream) {
+  DMVAE_CHECK_ARG(ctx && src_bits && idx && dst && rows >= 0 && D > 0, "gather_rows_bits: bad arguments");
+  const int vpr = (D + 127) / 128;
+  DMVAE_CHECK_ARG(D % 16 == 0 && dst_pitch_bytes >= D && dst_pitch_bytes % 16 == 0 && ((uintptr_t)dst & 15) == 0,
+                  "gather_rows_bits: D and the destination pitch must be multiples of 16, destination 16-byte aligned");
+  DMVAE_CHECK_ARG(src_pitch_bytes >= 16 * (int64_t)vpr && src_pitch_bytes % 16 == 0 && ((uintptr_t)src_bits & 15) == 0,
+                  "gather_rows_bits: packed rows must be padded to whole 16-byte pieces (pitch >= %d bytes, multiple of 16)", 16 * vpr);
+  if (rows == 0) return DMVAE_OK;
+  static bool carveout_set = false;          // same reason as dmvae_gather_rows: co-residence with the step's GEMM CTAs
+  if (!carveout_set) {
+    DMVAE_CUDA(cudaFuncSetAttribute(gather_bits_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    carveout_set = true;
+  }
+  const int64_t total = (int64_t)rows * vpr;
+  const int blocks = (int)max((int64_t)1, min((int64_t)32, (total + 255) / 256));
+  gather_bits_kernel<<<blocks, 128, 0, (cudaStream_t)stream>>>((const uint8_t*)src_bits, src_pitch_bytes, idx, (uint8_t*)dst,
+                                                                dst_pitch_bytes, rows, D, vpr);
+  DMVAE_LAUNCH_CHECK(ctx);
+  return DMVAE_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Adam, TensorFlow semantics: theta -= lr_t * m / (sqrt(v) + eps)
 // 16 B read (p,g,m,v) + 12 B written (p,m,v) per parameter (+2 B bf16 copy, +4 B gradient clear).

@@ -350,9 +350,9 @@ class DataParallel:
         self.eng.train_step(X, rows, opt, kl_ratio=kl_ratio)
 
     def run_epoch(self, host, batch_size, opt, kl_ratio=1.0, mode="all", max_steps=None, perm=None, while_busy=None,
-                  x_scale=1.0):
+                  x_scale=1.0, packed_D=0):
         """Every rank iterates over ITS host shard; the returned loss is the global mean (one all-reduce per epoch)."""
-        loss = self.eng.run_epoch(host, batch_size, opt, kl_ratio, mode, max_steps, perm, while_busy, x_scale)
+        loss = self.eng.run_epoch(host, batch_size, opt, kl_ratio, mode, max_steps, perm, while_busy, x_scale, packed_D)
         t = torch.tensor([loss], dtype=torch.float64, device=self.eng.device)
         dist.all_reduce(t, group=self.group)
         return float(t[0])

@@ -1522,8 +1522,9 @@ class Engine:
 
     def run_epoch(self, host: torch.Tensor, batch_size: int, opt: AdamState, kl_ratio: float = 1.0, mode: str = "all",
                   max_steps: Optional[int] = None, perm: Optional[np.ndarray] = None, while_busy=None,
-                  x_scale: float = 1.0) -> float:
-        """One pass over a (pinned) host array [N, D].  Per step, on a copy stream and double-buffered so that it overlaps
+                  x_scale: float = 1.0, packed_D: int = 0) -> float:
+        """One pass over a (pinned) host array [N, D] - or, with ``packed_D`` = D, over {0,1}-valued rows stored one bit per
+        element ([N, pitch] uint8 from includes/utils.py::_pack_bits), which the gather expands (dmvae_gather_rows_bits).  Per step, on a copy stream and double-buffered so that it overlaps
         the previous step: the batch's rows cross the bus into a staging buffer - a plain asynchronous copy of a
         contiguous slice, or with ``perm`` (the epoch's shuffle, includes/utils.py:450-454) a gather kernel that reads the
         rows ``perm[lo:lo+B]`` straight from the pinned host array (dmvae_gather_rows) - then the training step, and an
@@ -1537,6 +1538,10 @@ class Engine:
         dev = self.device
         if batch_size > self.max_rows:
             self._alloc_activations(batch_size)
+        if packed_D:
+            assert packed_D == self.D and host.dtype == torch.uint8
+            if perm is None:
+                perm = np.arange(N, dtype=np.int32)            # the expanding gather is index-driven
         key = (batch_size, host.dtype)
         if getattr(self, "_epoch_key", None) != key:
             self._epoch_key = key
@@ -1575,7 +1580,12 @@ class Engine:
             with torch.cuda.stream(self._copy_stream):
                 if i >= 2:
                     self._copy_stream.wait_event(self._free[b])
-                if perm_dev is None:
+                if packed_D:
+                    _abi.check(self.lib.dmvae_gather_rows_bits(self.ctx, host.data_ptr(), host.stride(0),
+                                                               perm_dev.data_ptr() + 4 * lo, self._stage[b].data_ptr(),
+                                                               self._stage[b].stride(0), rows, packed_D,
+                                                               C.c_void_p(self._copy_stream.cuda_stream)))
+                elif perm_dev is None:
                     self._stage[b][:rows].copy_(host[lo:lo + rows], non_blocking=True)
                 else:
                     _abi.check(self.lib.dmvae_gather_rows(self.ctx, host.data_ptr(), host.stride(0) * host.element_size(),
@@ -1607,7 +1617,7 @@ class Engine:
 
     def run_epoch_moe(self, host_x: torch.Tensor, host_y: torch.Tensor, batch_size: int, opt: AdamState, kl_ratio: float = 1.0,
                       perm: Optional[np.ndarray] = None, max_steps: Optional[int] = None, while_busy=None,
-                      x_scale: float = 1.0) -> np.ndarray:
+                      x_scale: float = 1.0, packed_D: int = 0) -> np.ndarray:
         """One pass of the MoE training step (models.py:194-221) over pinned host arrays X [N, D] / Y [N, O], batches staged
         like run_epoch.  Returns per-step [supervised loss sum, error sum, recon, KL_c, KL_z, VAE loss] as a host array."""
         N = host_x.shape[0]
@@ -1619,6 +1629,10 @@ class Engine:
         dev = self.device
         if batch_size > self.max_rows:
             self._alloc_activations(batch_size)
+        if packed_D:
+            assert packed_D == self.D and host_x.dtype == torch.uint8
+            if perm is None:
+                perm = np.arange(N, dtype=np.int32)
         key = ("moe", batch_size, host_x.dtype, O)
         if getattr(self, "_epoch_key", None) != key:
             self._epoch_key = key
@@ -1657,7 +1671,12 @@ class Engine:
                     self._stage_y[b][:rows].copy_(host_y[lo:lo + rows], non_blocking=True)
                 else:
                     ix = perm_dev.data_ptr() + 4 * lo
-                    _abi.check(self.lib.dmvae_gather_rows(self.ctx, host_x.data_ptr(), xb, ix, self._stage[b].data_ptr(), xb, rows, xb, cs))
+                    if packed_D:
+                        _abi.check(self.lib.dmvae_gather_rows_bits(self.ctx, host_x.data_ptr(), host_x.stride(0), ix,
+                                                                   self._stage[b].data_ptr(), self._stage[b].stride(0), rows,
+                                                                   packed_D, cs))
+                    else:
+                        _abi.check(self.lib.dmvae_gather_rows(self.ctx, host_x.data_ptr(), xb, ix, self._stage[b].data_ptr(), xb, rows, xb, cs))
                     _abi.check(self.lib.dmvae_gather_rows(self.ctx, host_y.data_ptr(), yb, ix, self._stage_y[b].data_ptr(), yb, rows, yb, cs))
                 self._ready[b].record(self._copy_stream)
             cur.wait_event(self._ready[b])

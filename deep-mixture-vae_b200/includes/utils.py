@@ -8,6 +8,7 @@ host->device copy per batch instead of the reference's per-row Python append (ut
 from __future__ import annotations
 
 import math
+import os
 from typing import Optional
 
 import numpy as np
@@ -166,6 +167,20 @@ def _storage_format(data: np.ndarray):
     return np.float32, 1.0
 
 
+def _pack_bits(data: np.ndarray):
+    """{0,1}-valued rows at one bit per element (numpy little bit order), each row padded with zero bytes to a multiple of
+    16 bytes: what dmvae_gather_rows_bits expands on the device.  None when the data is not binary or D % 16 != 0."""
+    if os.environ.get("DMVAE_PACK_BITS", "1") == "0":          # A/B switch: move uint8 rows instead
+        return None
+    if not data.size or data.shape[1] % 16 or not np.all((data == 0) | (data == 1)):
+        return None
+    bits = np.packbits(data.astype(bool), axis=1, bitorder="little")
+    pitch = (bits.shape[1] + 15) // 16 * 16
+    out = np.zeros((data.shape[0], pitch), np.uint8)
+    out[:, :bits.shape[1]] = bits
+    return out
+
+
 def _storage_dtype(data: np.ndarray):
     return _storage_format(data)[0]
 
@@ -220,6 +235,14 @@ class Dataset:
 
     host_scale = 1.0        # value of one unit of host_tensor() (1/255 for 8-bit intensities stored as uint8)
 
+    def host_bits(self):
+        """(pinned [N, pitch] uint8 holding the rows at ONE BIT per element, D) for binarised data, else None; built once.
+        The training path moves these 8x fewer bytes per batch and expands them on the device."""
+        if not hasattr(self, "_bits"):
+            packed = _pack_bits(self.data) if self._compact else None
+            self._bits = None if packed is None else (_pinned(packed, np.uint8), self.data.shape[1])
+        return self._bits
+
     def begin_epoch(self):
         """New epoch order, drawn like get_batches does at the start of every epoch (utils.py:450-454)."""
         if self.shuffle:
@@ -264,6 +287,13 @@ class MEDataset:
         return self._host
 
     host_scale = 1.0
+
+    def host_bits(self):
+        """Like Dataset.host_bits, for the expert models' inputs."""
+        if not hasattr(self, "_bits"):
+            packed = _pack_bits(self.data)
+            self._bits = None if packed is None else (_pinned(packed, np.uint8), self.data.shape[1])
+        return self._bits
 
     def begin_epoch(self):
         if self.shuffle:

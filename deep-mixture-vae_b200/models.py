@@ -185,8 +185,13 @@ class MoE:
         opt = eng.optimizer("moe", self._lr["moe"])
         data.begin_epoch()
         hx, hy = data.host_tensors()
-        log = eng.run_epoch_moe(hx, hy, data.batch_size, opt, kl_ratio, perm=data.perm, while_busy=data.prefetch_epoch,
-                                x_scale=data.host_scale)
+        bits = data.host_bits()
+        if bits is not None:                                    # binarised inputs: one bit per element over the bus
+            log = eng.run_epoch_moe(bits[0], hy, data.batch_size, opt, kl_ratio, perm=data.perm,
+                                    while_busy=data.prefetch_epoch, x_scale=1.0, packed_D=bits[1])
+        else:
+            log = eng.run_epoch_moe(hx, hy, data.batch_size, opt, kl_ratio, perm=data.perm, while_busy=data.prefetch_epoch,
+                                    x_scale=data.host_scale)
         nb = len(log)
         last_rows = data.len - (nb - 1) * data.batch_size if nb == data.epoch_len else data.batch_size
         rows = np.full(nb, data.batch_size, np.float64)

@@ -131,6 +131,11 @@ int dmvae_stage_input(dmvae_ctx* ctx, const void* X, int x_dtype, int64_t ldx, v
  * rows cross the bus exactly once); dst is device memory.  Rows and pitches must be 4-byte multiples (16 for speed). */
 int dmvae_gather_rows(dmvae_ctx* ctx, const void* src, int64_t src_pitch_bytes, const int32_t* idx, void* dst,
                       int64_t dst_pitch_bytes, int rows, int row_bytes, void* stream);
+/* The same for {0,1}-valued rows kept ONE BIT per element on the host (numpy.packbits(..., bitorder="little"), each row
+ * padded with zero bytes to a multiple of 16 bytes): dst[r, :D] = the bits of packed row idx[r] as uint8 0/1.  8x fewer bytes
+ * over the bus. */
+int dmvae_gather_rows_bits(dmvae_ctx* ctx, const void* src_bits, int64_t src_pitch_bytes, const int32_t* idx, void* dst,
+                           int64_t dst_pitch_bytes, int rows, int D, void* stream);
 
 /* ---- reparameterisation: priors.py:86-89 (Z), :170-181 (concrete), utils.py:17-19 (Gumbel),
  *      host RNG of priors.py:67-68 replaced by Philox4x32-10 ------------------------------------ */

@@ -22,19 +22,25 @@ def main():
     ap.add_argument("--config", type=int, default=2)
     ap.add_argument("--steps", type=int, default=24)
     ap.add_argument("--full", action="store_true", help="print every kernel of the last two steps")
+    ap.add_argument("--packed", action="store_true", help="binarised rows at one bit per element (dmvae_gather_rows_bits)")
     a = ap.parse_args()
     cfg = configs.CONFIGS[a.config]
     B = cfg["batch"]
     eng = configs.make_engine(cfg, B)
     opt = eng.optimizer("train", 0.002)
     N = a.steps * B
-    host = torch.from_numpy(configs.synth_inputs(cfg, N)).pin_memory()
+    X = configs.synth_inputs(cfg, N)
+    kw = dict(x_scale=configs.x_scale(cfg))
+    if a.packed:
+        from dmvae_b200.includes.utils import _pack_bits
+        X, kw = _pack_bits(X), dict(x_scale=1.0, packed_D=cfg["D"])
+    host = torch.from_numpy(X).pin_memory()
     rs = np.random.RandomState(0)
     for _ in range(2):
-        eng.run_epoch(host, B, opt, perm=rs.permutation(N), x_scale=configs.x_scale(cfg))
+        eng.run_epoch(host, B, opt, perm=rs.permutation(N), **kw)
     torch.cuda.synchronize()
     with profile(activities=[ProfilerActivity.CUDA]) as prof:
-        eng.run_epoch(host, B, opt, perm=rs.permutation(N), x_scale=configs.x_scale(cfg))
+        eng.run_epoch(host, B, opt, perm=rs.permutation(N), **kw)
         torch.cuda.synchronize()
     out = os.path.join(ROOT, "gpurun_out", "epoch_trace.json")
     os.makedirs(os.path.dirname(out), exist_ok=True)
@@ -42,7 +48,7 @@ def main():
     ev = [e for e in json.load(open(out))["traceEvents"] if e.get("cat") in ("kernel", "gpu_memcpy", "gpu_memset")]
     ev.sort(key=lambda e: e["ts"])
     ticks = [e["ts"] for e in ev if "step_tick" in e["name"]]
-    gath = [e for e in ev if "gather_rows" in e["name"]]
+    gath = [e for e in ev if "gather_" in e["name"]]
     print("%s: %d steps, %d gathers" % (cfg["name"], len(ticks), len(gath)))
     iv = np.diff(ticks)
     print("step start-to-start us: median %.1f  min %.1f  max %.1f  first five %s" %

@@ -220,3 +220,28 @@ def test_decode_and_reconstruct_entry_points(gd, tol):
 def relerr_(got, ref):
     got, ref = np.asarray(got, np.float64), np.asarray(ref, np.float64)
     return float(np.abs(got - ref).max() / max(np.abs(ref).max(), 1e-30))
+
+
+def test_bit_packed_rows_expand_to_the_same_batch():
+    """dmvae_gather_rows_bits: {0,1} rows kept one bit per element on the host come out as the uint8 batch the byte gather
+    gives, for a permuted index list and a ragged width (D % 32 == 16)."""
+    import ctypes as C
+    from dmvae_b200 import _abi
+    from dmvae_b200.includes.utils import _pack_bits
+    lib = _abi.load()
+    ctx = C.c_void_p()
+    _abi.check(lib.dmvae_ctx_create(0, C.byref(ctx)))
+    rs = np.random.RandomState(3)
+    for N, D, B in ((500, 784, 129), (64, 3072, 64), (40, 16, 7)):
+        X = (rs.uniform(size=(N, D)) < 0.3).astype(np.uint8)
+        packed = _pack_bits(X)
+        assert packed is not None and packed.shape[1] % 16 == 0
+        host = torch.from_numpy(packed).pin_memory()
+        idx = rs.permutation(N)[:B].astype(np.int32)
+        idx_d = torch.tensor(idx, device="cuda")
+        out = torch.full((B, D), 7, dtype=torch.uint8, device="cuda")
+        _abi.check(lib.dmvae_gather_rows_bits(ctx, host.data_ptr(), host.stride(0), idx_d.data_ptr(), out.data_ptr(), out.stride(0),
+                                              B, D, None))
+        torch.cuda.synchronize()
+        assert np.array_equal(out.cpu().numpy(), X[idx])
+    lib.dmvae_ctx_destroy(ctx)

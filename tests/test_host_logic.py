@@ -222,3 +222,16 @@ def test_dataset_storage_format_and_epoch_order():
     me = MEDataset((xb, np.arange(50), np.eye(5)[np.arange(50) % 5]), batch_size=20)
     got = list(me.get_batches())
     assert np.array_equal(np.concatenate([g[2] for g in got]), me.perm) and got[0][1].shape == (20, 5)
+
+
+def test_pack_bits_layout():
+    """includes/utils.py::_pack_bits: little bit order, rows padded to 16 bytes, None for non-binary data."""
+    from dmvae_b200.includes.utils import _pack_bits
+    rs = np.random.RandomState(0)
+    X = (rs.uniform(size=(5, 784)) < 0.5).astype(np.float32)
+    p = _pack_bits(X)
+    assert p.shape == (5, 112) and p.dtype == np.uint8 and not p[:, 98:].any()
+    back = np.unpackbits(p[:, :98], axis=1, bitorder="little")[:, :784]
+    assert np.array_equal(back, X.astype(np.uint8))
+    assert _pack_bits(rs.uniform(size=(4, 32)).astype(np.float32)) is None
+    assert _pack_bits(np.zeros((4, 20), np.float32)) is None          # width not a multiple of 16
