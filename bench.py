@@ -370,7 +370,7 @@ def run_ours(args):
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": world * B * h2d_row_bytes + (world * B * cfg.get("output_dim", 0) * 4 if is_moe else 0),
                 "d2h_bytes_per_step": world * (24 if is_moe else 16), "ms_per_step": ms_e2e / K_,
                 "api": "model.train_op(Session(), %s(...)): %d epochs of %d batches; rows gathered by permutation index from the "
-                       "pinned host array by a copy-stream kernel (zero-copy reads%s), loss terms read back per epoch from a device ring"
+                       "pinned host array by a copy-stream kernel (zero-copy reads%s), every step writes its loss terms into a pinned host ring (16 B device -> host per step)"
                        % ("MEDataset" if is_moe else "Dataset", K_ // nb_host, nb_host,
                           "; binarised rows stored one bit per element on the host and expanded by the gather" if bits is not None else "")},
         "gpu_launches": int(launches),

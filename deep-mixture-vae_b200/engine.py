@@ -473,9 +473,10 @@ class Engine:
         self.f_scratch = z(2 * self.L, f32)
         if getattr(self, "loss_out", None) is None:
             self.loss_out = torch.zeros(4, dtype=f32, device=dev)      # allocated once: fetches keep reading the same scalar block
-            # loss terms of the last LOSS_RING steps, slot = step counter % LOSS_RING (dmvae_log_append): run_epoch reads an
-            # epoch's losses from here after its last step
-            self.loss_ring = torch.zeros(self.LOSS_RING, 4, dtype=f32, device=dev)
+            # loss terms of the last LOSS_RING steps, slot = step counter % LOSS_RING (dmvae_log_append).  The ring is PINNED
+            # HOST memory: every captured step writes its 16 bytes across the bus itself (the per-step device -> host read of
+            # the loss), and run_epoch only has to look at them after its final synchronisation
+            self.loss_ring = torch.zeros(self.LOSS_RING, 4, dtype=f32).pin_memory()
         ws = int(self.lib.dmvae_elbo_reduce_workspace(B, self.L, self.K))
         self.red_ws = torch.zeros(max(ws, 4), dtype=f32, device=dev)
         self.x_stage: Dict[int, torch.Tensor] = {}
@@ -491,7 +492,7 @@ class Engine:
             self.moe_dinp = z(self.layers["moe"].in_pad, f32)
             self.y_buf = z(O, f32)
             self.moe_loss = torch.zeros(2, dtype=f32, device=dev)
-            self.moe_ring = torch.zeros(self.LOSS_RING, 2, dtype=f32, device=dev)
+            self.moe_ring = torch.zeros(self.LOSS_RING, 2, dtype=f32).pin_memory()    # pinned host memory, like loss_ring
 
     LOSS_RING = 4096
 
@@ -1599,20 +1600,16 @@ class Engine:
             if not ring:
                 self._loss_log[i].copy_(self.loss_out, non_blocking=True)
             self._free[b].record(cur)
-        if ring:
-            # the steps filed their loss terms in the ring themselves (slot = step counter): one gather after the last step
-            # (consecutive slots: one or two slices, no index upload - that would make the host wait for the epoch here,
-            # before while_busy)
-            first = slots[0]
-            n1 = min(nb, self.LOSS_RING - first)
-            self._loss_log[:n1].copy_(self.loss_ring[first:first + n1], non_blocking=True)
-            if n1 < nb:
-                self._loss_log[n1:nb].copy_(self.loss_ring[:nb - n1], non_blocking=True)
-        self._loss_host[:nb].copy_(self._loss_log[:nb], non_blocking=True)
+        if not ring:
+            self._loss_host[:nb].copy_(self._loss_log[:nb], non_blocking=True)
         if while_busy is not None:
             while_busy()                           # host work hidden behind the queued steps (e.g. the next epoch's shuffle)
         cur.synchronize()
         col = {"all": 3, "vae": 0, "prior": 3}[mode]
+        if ring:
+            # the steps wrote their loss terms into the pinned ring themselves (slot = step counter): just read them
+            idx = (slots[0] + np.arange(nb)) % self.LOSS_RING
+            return float(self.loss_ring.numpy()[idx, col].astype(np.float64).sum()) / nb
         return float(self._loss_host[:nb, col].sum()) / nb
 
     def run_epoch_moe(self, host_x: torch.Tensor, host_y: torch.Tensor, batch_size: int, opt: AdamState, kl_ratio: float = 1.0,
@@ -1687,18 +1684,15 @@ class Engine:
                 self._moe_log[i, :2].copy_(self.moe_loss, non_blocking=True)
                 self._moe_log[i, 2:].copy_(self.loss_out, non_blocking=True)
             self._free[b].record(cur)
-        if ring and nb > 0:
-            # the captured steps filed their loss blocks in the rings (slot = step counter): consecutive slots, two slices at most
-            n1 = min(nb, self.LOSS_RING - first)
-            self._moe_log[:n1, :2].copy_(self.moe_ring[first:first + n1], non_blocking=True)
-            self._moe_log[:n1, 2:].copy_(self.loss_ring[first:first + n1], non_blocking=True)
-            if n1 < nb:
-                self._moe_log[n1:nb, :2].copy_(self.moe_ring[:nb - n1], non_blocking=True)
-                self._moe_log[n1:nb, 2:].copy_(self.loss_ring[:nb - n1], non_blocking=True)
-        self._moe_log_host[:nb].copy_(self._moe_log[:nb], non_blocking=True)
+        if not ring:
+            self._moe_log_host[:nb].copy_(self._moe_log[:nb], non_blocking=True)
         if while_busy is not None:
             while_busy()
         cur.synchronize()
+        if ring:
+            # the captured steps wrote their loss blocks into the pinned rings (slot = step counter)
+            idx = (first + np.arange(nb)) % self.LOSS_RING
+            return np.concatenate([self.moe_ring.numpy()[idx], self.loss_ring.numpy()[idx]], axis=1)
         return self._moe_log_host[:nb].numpy().copy()
 
     def launches(self) -> int:
