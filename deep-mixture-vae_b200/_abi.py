@@ -166,7 +166,7 @@ def load():
         fn = getattr(lib, name)          # AttributeError here = header/library mismatch: fail loudly
         fn.restype = res
         fn.argtypes = args
-    if lib.dmvae_abi_version() != 1:
+    if lib.dmvae_abi_version() != 2:
         raise ImportError("libdmvae_b200.so ABI version mismatch")
     _lib = lib
     return lib

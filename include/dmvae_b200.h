@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define DMVAE_B200_ABI_VERSION 1
+#define DMVAE_B200_ABI_VERSION 2   /* 2: dmvae_gemm_epilogue.recon, dmvae_elbo_args.r_part, dmvae_reparam_args.fold_*, x_scale arguments */
 
 typedef struct dmvae_ctx dmvae_ctx;
 

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), "libdmvae_b200.so does not export %s" % name
     assert declared == set(_abi.SIGNATURES.keys()), declared ^ set(_abi.SIGNATURES.keys())
-    assert _abi.load().dmvae_abi_version() == 1
+    assert _abi.load().dmvae_abi_version() == 2
 
 
 def test_abi_structs_match_c_layout():
