@@ -252,9 +252,7 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        # stdout carries exactly one JSON line: NCCL's own banner ("NCCL version ...", printed when NCCL_DEBUG is set in the
-        # environment) goes to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        # (NCCL prints its "NCCL version ..." banner on stdout at communicator creation; the JSON line is the LAST line)
         dist.init_process_group("nccl", device_id=dev)
     strong = cfg["scaling"] == "strong"
     B = cfg["batch"] // world if strong else cfg["batch"]           # rows per GPU
